@@ -1,0 +1,665 @@
+/* acm_device.cu -- GPU side of libac75.so: device images, scan pipelines, batch C-ABI (include/acm_b200.h).
+ *
+ * There is deliberately no CPU implementation of the batch scan in this library: without a CUDA device every entry point
+ * returns ACM_B200_ERR_NO_DEVICE.
+ */
+#include "acm_internal.h"
+#include "acm_kernels.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace acm;
+
+static thread_local char g_error[512] = "";
+
+static int
+fail (int code, const char *fmt, const char *a = "", const char *b = "") {
+  snprintf (g_error, sizeof g_error, fmt, a, b);
+  return code;
+}
+
+#define CUDA_TRY(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail (ACM_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString (e_));     \
+  } while (0)
+
+extern "C" const char *
+acm_b200_last_error (void) {
+  return g_error;
+}
+
+extern "C" const char *
+acm_b200_version (void) {
+  return "ac75-b200 0.1 (sm_100a)";
+}
+
+extern "C" int
+acm_b200_device_count (void) {
+  int n = 0;
+  if (cudaGetDeviceCount (&n) != cudaSuccess) {
+    cudaGetLastError ();
+    return 0;
+  }
+  return n;
+}
+
+/* grow-only device buffer */
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int ensure (size_t want) {
+    if (want <= bytes)
+      return ACM_B200_OK;
+    if (ptr)
+      cudaFree (ptr);
+    ptr = nullptr;
+    bytes = 0;
+    size_t grown = want + want / 8 + 256;
+    cudaError_t e = cudaMalloc (&ptr, grown);
+    if (e != cudaSuccess) {
+      cudaGetLastError ();
+      e = cudaMalloc (&ptr, grown = want);
+    }
+    if (e != cudaSuccess)
+      return fail (ACM_B200_ERR_NOMEM, "cudaMalloc of %s bytes failed: %s", std::to_string (want).c_str (), cudaGetErrorString (e));
+    bytes = grown;
+    return ACM_B200_OK;
+  }
+  void release () {
+    if (ptr)
+      cudaFree (ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T *as () const { return reinterpret_cast<T *> (ptr); }
+};
+
+struct acm_device_image {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_edges;
+  DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_tile_first, d_tile_n, d_small;
+  struct Small { /* one pinned + one device copy of the scalars the kernels write */
+    unsigned long long cand_count;
+    uint64_t grand_total;
+    uint32_t overflow;
+    uint32_t pad;
+    uint32_t prefix[1024];
+  } *h_small = nullptr;
+  ACMB200Stats stats = {};
+};
+
+extern "C" void
+acm_device_release (struct acm_device_image *img) {
+  if (!img)
+    return;
+  cudaSetDevice (img->device);
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_edges, &img->d_text, &img->d_matches,
+                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_tile_first, &img->d_tile_n, &img->d_small })
+    b->release ();
+  for (cudaEvent_t e : img->ev)
+    if (e)
+      cudaEventDestroy (e);
+  if (img->stream)
+    cudaStreamDestroy (img->stream);
+  if (img->h_small)
+    cudaFreeHost (img->h_small);
+  acm_free_tables (&img->tab);
+  delete img;
+}
+
+static int
+upload (DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
+  int rc = dst.ensure (bytes ? (bytes + 15) / 16 * 16 : 16);
+  if (rc)
+    return rc;
+  if (bytes)
+    CUDA_TRY (cudaMemcpyAsync (dst.ptr, src, bytes, cudaMemcpyHostToDevice, st));
+  return ACM_B200_OK;
+}
+
+/* ---- finalise ------------------------------------------------------------------------------------------------------- */
+static int
+finalise_locked (ACMachine *m, int device) {
+  if (acm_b200_device_count () <= 0)
+    return fail (ACM_B200_ERR_NO_DEVICE, "no CUDA device is available: the batch scan has no CPU fallback");
+  acm_device_image *img = m->device;
+  if (img && device >= 0 && img->device != device) {
+    acm_device_release (img);
+    img = m->device = nullptr;
+  }
+  if (!img) {
+    if (device < 0)
+      CUDA_TRY (cudaGetDevice (&device));
+    CUDA_TRY (cudaSetDevice (device));
+    img = new acm_device_image ();
+    m->device = img;
+    m->device_generation = 0;
+    img->device = device;
+    int v = 0;
+    CUDA_TRY (cudaDeviceGetAttribute (&v, cudaDevAttrMultiProcessorCount, device));
+    img->sm_count = v;
+    CUDA_TRY (cudaDeviceGetAttribute (&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    img->smem_optin = (size_t)v;
+    CUDA_TRY (cudaStreamCreateWithFlags (&img->stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : img->ev)
+      CUDA_TRY (cudaEventCreate (&e));
+    CUDA_TRY (cudaMallocHost (&img->h_small, sizeof (*img->h_small)));
+    int rc = img->d_small.ensure (sizeof (*img->h_small));
+    if (rc)
+      return rc;
+  } else
+    CUDA_TRY (cudaSetDevice (img->device));
+  if (m->device_generation == m->generation)
+    return ACM_B200_OK;
+
+  const auto t0 = std::chrono::steady_clock::now ();
+  acm_free_tables (&img->tab);
+  /* shared-memory budget for the resident table: everything a block may opt in to, minus class map / staging / slack */
+  const uint64_t budget = img->smem_optin - 32 * 256 * 2 - 2048;
+  int rc = acm_build_tables (m, &img->tab, budget);
+  if (rc)
+    return fail (rc, "building the automaton tables failed%s", "");
+  acm_tables &t = img->tab;
+  cudaStream_t st = img->stream;
+  uint64_t bytes = 0;
+  if (t.engine == ACM_B200_ENGINE_FILTER) {
+    if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
+        || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st)))
+      return rc;
+    bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot);
+  } else {
+    if ((rc = upload (img->d_delta, t.delta, t.delta_bytes, st)) || (rc = upload (img->d_out_offsets, t.out_offsets, ((size_t)t.nb_dfa_states - t.out_threshold + 1) * 4, st))
+        || (rc = upload (img->d_out_entries, t.out_entries, t.nb_out_entries * sizeof (acm_output), st)))
+      return rc;
+    bytes = t.delta_bytes + ((uint64_t)t.nb_dfa_states - t.out_threshold + 1) * 4 + t.nb_out_entries * sizeof (acm_output);
+  }
+  CUDA_TRY (cudaStreamSynchronize (st));
+  /* the big host images are not needed any more */
+  free (t.delta), t.delta = nullptr;
+  free (t.out_offsets), t.out_offsets = nullptr;
+  free (t.out_entries), t.out_entries = nullptr;
+  free (t.bloom), t.bloom = nullptr;
+  free (t.qgrams), t.qgrams = nullptr;
+  free (t.edges), t.edges = nullptr;
+  m->device_generation = m->generation;
+  ACMB200Stats &s = img->stats;
+  s.engine = t.engine;
+  s.symbol_width = t.width;
+  s.nb_states = t.nb_states;
+  s.nb_keywords = t.nb_keywords;
+  s.max_keyword_length = t.lmax;
+  s.min_keyword_length = t.lmin;
+  s.nb_classes = t.nb_classes;
+  s.table_bytes = bytes;
+  s.finalise_count++;
+  s.finalise_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count ();
+  return ACM_B200_OK;
+}
+
+extern "C" int
+acm_b200_finalise (ACMachine *m, int device) {
+  if (!m)
+    return fail (ACM_B200_ERR_INVALID, "null machine%s", "");
+  acm_lock (m);
+  int rc = finalise_locked (m, device);
+  acm_unlock (m);
+  return rc;
+}
+
+extern "C" int
+acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
+  if (!m || !key || !value)
+    return ACM_B200_ERR_INVALID;
+  acm_lock (m);
+  int rc = ACM_B200_OK;
+  if (!strcmp (key, "engine")) {
+    snprintf (m->engine_override, sizeof m->engine_override, "%s", strcmp (value, "auto") ? value : "");
+    m->generation++; /* forces a rebuild */
+  } else if (!strcmp (key, "tile_rows"))
+    m->option_tile_rows = strtoull (value, 0, 10);
+  else if (!strcmp (key, "bloom_words"))
+    m->option_bloom_words = strtoull (value, 0, 10), m->generation++;
+  else if (!strcmp (key, "bloom_k"))
+    m->option_bloom_k = strtoull (value, 0, 10), m->generation++;
+  else if (!strcmp (key, "threads"))
+    m->option_threads = strtoull (value, 0, 10);
+  else
+    rc = ACM_B200_ERR_INVALID;
+  acm_unlock (m);
+  return rc;
+}
+
+extern "C" int
+acm_b200_get_stats (ACMachine *m, ACMB200Stats *stats) {
+  if (!m || !stats)
+    return ACM_B200_ERR_INVALID;
+  if (m->device)
+    *stats = m->device->stats;
+  else
+    memset (stats, 0, sizeof (*stats));
+  return ACM_B200_OK;
+}
+
+/* ---- device scan of counts ------------------------------------------------------------------------------------------ */
+static int
+device_exclusive_scan (acm_device_image *img, const uint32_t *counts, uint64_t n, uint64_t *offsets, uint64_t *d_grand, cudaStream_t st) {
+  const uint64_t nblocks = (n + kScanBlock - 1) / kScanBlock;
+  int rc = img->d_block_sums.ensure ((nblocks + 1) * 8);
+  if (rc)
+    return rc;
+  uint64_t *sums = img->d_block_sums.as<uint64_t> ();
+  scan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>> (counts, n, sums);
+  scan_spine_kernel<<<1, kScanThreads, 0, st>>> (sums, nblocks, d_grand);
+  scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>> (counts, n, sums, offsets);
+  img->stats.total_kernel_launches += 3;
+  CUDA_TRY (cudaGetLastError ());
+  return ACM_B200_OK;
+}
+
+struct ScanJob {
+  const void *d_text;
+  uint64_t n, lead, base;
+  ACMB200Match *d_matches; /* device buffer of `capacity` records, or null while only counting */
+  uint64_t capacity;
+  uint32_t init_dfa_state;
+  uint32_t prefix_len; /* symbols staged in h_small->prefix */
+  cudaStream_t st;
+};
+
+/* ---- DFA pipeline --------------------------------------------------------------------------------------------------- */
+template <typename Entry, bool kShared>
+static int
+run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+  const acm_tables &t = img->tab;
+  DfaParams p = {};
+  p.text = reinterpret_cast<const uint8_t *> (job.d_text);
+  p.n = job.n;
+  p.lead = job.lead;
+  p.base = job.base;
+  p.warm = m->max_depth ? m->max_depth - 1 : 0;
+  p.init_state = job.init_dfa_state;
+  p.delta = img->d_delta.ptr;
+  p.K = t.nb_classes;
+  p.nb_states = t.nb_dfa_states;
+  p.out_threshold = t.out_threshold;
+  p.out_offsets = img->d_out_offsets.as<uint32_t> ();
+  p.out_entries = img->d_out_entries.as<acm_output> ();
+  memcpy (p.class_of_byte, t.class_of_byte, 256);
+
+  const int threads = kShared ? 1024 : 256;
+  const size_t smem = 256 + (kShared ? ((size_t)t.nb_dfa_states * t.nb_classes * sizeof (Entry) + 15) / 16 * 16 : 0);
+  const int blocks_per_sm = kShared ? 1 : 8;
+  uint64_t want_threads = m->option_threads ? m->option_threads : (uint64_t)img->sm_count * blocks_per_sm * threads;
+  const uint64_t min_chunk = std::max<uint64_t> (256, (uint64_t)(4 * p.warm + 15) / 16 * 16);
+  p.chunk = std::max<uint64_t> (min_chunk, ((job.n + want_threads - 1) / want_threads + 15) / 16 * 16);
+  p.nchunks = (job.n + p.chunk - 1) / p.chunk;
+  const unsigned grid = (unsigned)std::min<uint64_t> ((p.nchunks + threads - 1) / threads, (uint64_t)img->sm_count * blocks_per_sm);
+
+  int rc;
+  if ((rc = img->d_counts.ensure (p.nchunks * 4)) || (rc = img->d_offsets.ensure (p.nchunks * 8)))
+    return rc;
+  p.chunk_counts = img->d_counts.as<uint32_t> ();
+  p.chunk_offsets = img->d_offsets.as<uint64_t> ();
+  auto *d_small = img->d_small.as<acm_device_image::Small> ();
+
+  auto count_k = dfa_scan_kernel<Entry, kShared, false>;
+  auto emit_k = dfa_scan_kernel<Entry, kShared, true>;
+  CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  img->stats.smem_bytes = smem;
+
+  CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+  count_k<<<grid, threads, smem, job.st>>> (p);
+  CUDA_TRY (cudaGetLastError ());
+  CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
+  if ((rc = device_exclusive_scan (img, p.chunk_counts, p.nchunks, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+    return rc;
+  CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
+  CUDA_TRY (cudaStreamSynchronize (job.st));
+  *total = img->h_small->grand_total;
+  img->stats.main_kernel_launches += 1;
+  img->stats.total_kernel_launches += 1;
+
+  const uint64_t want = std::min<uint64_t> (*total, job.capacity);
+  CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+  if (want) {
+    if (matches_on_device)
+      p.matches = user_matches;
+    else {
+      if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
+        return rc;
+      p.matches = img->d_matches.as<ACMB200Match> ();
+    }
+    p.capacity = want;
+    emit_k<<<grid, threads, smem, job.st>>> (p);
+    CUDA_TRY (cudaGetLastError ());
+    img->stats.main_kernel_launches += 1;
+    img->stats.total_kernel_launches += 1;
+  }
+  CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+  job.d_matches = p.matches;
+  img->stats.last_nb_candidates = 0;
+  return ACM_B200_OK;
+}
+
+/* ---- filter pipeline ------------------------------------------------------------------------------------------------ */
+template <int W>
+static int
+run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+  const acm_tables &t = img->tab;
+  constexpr int kRows = 4;
+  auto *d_small = img->d_small.as<acm_device_image::Small> ();
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const bool dense = attempt == 1; /* second try: no candidate buffer can overflow */
+    FilterParams p = {};
+    p.text = job.d_text;
+    p.n = job.n;
+    p.lead = job.lead;
+    p.base = job.base;
+    p.q = t.q;
+    p.tile_rows = kRows;
+    p.tile_syms = kRows * 512 / W;
+    p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
+    p.bloom = img->d_bloom.as<uint32_t> ();
+    p.bloom_words = t.bloom_words;
+    p.bloom_k = t.bloom_k;
+    p.qgrams = img->d_qgrams.as<acm_slot> ();
+    p.qgram_mask = t.qgram_slots - 1;
+    p.edges = img->d_edges.as<acm_slot> ();
+    p.edge_mask = t.edge_slots - 1;
+    p.prefix = d_small->prefix;
+    p.prefix_len = job.prefix_len;
+    p.stage_cap = dense ? p.tile_syms : 256;
+    p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / 32, 1u << 16);
+    size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2;
+    int warps = 32;
+    while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
+      warps /= 2;
+    const size_t smem = (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp;
+    if (smem > img->smem_optin)
+      return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
+    int rc;
+    if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
+        || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
+      return rc;
+    p.cand_pos = img->d_cand_pos.as<uint64_t> ();
+    p.cand_matches = img->d_cand_matches.as<uint32_t> ();
+    p.tile_first = img->d_tile_first.as<uint64_t> ();
+    p.tile_n = img->d_tile_n.as<uint32_t> ();
+    p.tile_matches = img->d_counts.as<uint32_t> ();
+    p.tile_offsets = img->d_offsets.as<uint64_t> ();
+    p.cand_count = &d_small->cand_count;
+    p.overflow = &d_small->overflow;
+
+    auto f1 = filter_scan_kernel<W, kRows>;
+    CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    img->stats.smem_bytes = smem;
+    /* header of Small (cand_count, grand_total, overflow) cleared; the prefix symbols follow */
+    img->h_small->cand_count = 0;
+    img->h_small->grand_total = 0;
+    img->h_small->overflow = 0;
+    CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
+    const unsigned grid = (unsigned)std::min<uint64_t> ((p.ntiles + warps - 1) / warps, (uint64_t)img->sm_count);
+    CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+    f1<<<grid, warps * 32, smem, job.st>>> (p);
+    CUDA_TRY (cudaGetLastError ());
+    CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
+    const unsigned vgrid = (unsigned)((p.ntiles + 255) / 256);
+    filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p);
+    CUDA_TRY (cudaGetLastError ());
+    if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+      return rc;
+    CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
+    CUDA_TRY (cudaStreamSynchronize (job.st));
+    img->stats.main_kernel_launches += 1;
+    img->stats.total_kernel_launches += 2;
+    if (img->h_small->overflow) {
+      img->stats.fallback_count++;
+      if (dense)
+        return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
+      continue;
+    }
+    *total = img->h_small->grand_total;
+    img->stats.last_nb_candidates = img->h_small->cand_count;
+    const uint64_t want = std::min<uint64_t> (*total, job.capacity);
+    CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+    if (want) {
+      if (matches_on_device)
+        p.matches = user_matches;
+      else {
+        if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
+          return rc;
+        p.matches = img->d_matches.as<ACMB200Match> ();
+      }
+      p.capacity = want;
+      filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p);
+      CUDA_TRY (cudaGetLastError ());
+      img->stats.total_kernel_launches += 1;
+    }
+    CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+    job.d_matches = p.matches;
+    return ACM_B200_OK;
+  }
+  return fail (ACM_B200_ERR_CUDA, "unreachable%s", "");
+}
+
+/* ---- cursor bookkeeping (host, at most max_depth symbols) ------------------------------------------------------------ */
+static const ACState *
+advance_cursor (ACMachine *m, const ACState *from, const unsigned char *tail, uint64_t tail_syms, bool tail_is_whole_text) {
+  /* The state after the text is the longest suffix of (string(from) + text) that is a trie path; it is at most max_depth long, so
+   * the last max_depth symbols decide it when the text is at least that long (walk from state 0), else walk everything from `from`. */
+  const ACState *s = tail_is_whole_text ? from : m->root;
+  const size_t w = acm_b200_symbol_width (m);
+  const bool raw = m->symbol_kind == ACM_SYM_RAW1 || m->symbol_kind == ACM_SYM_RAW2 || m->symbol_kind == ACM_SYM_RAW4;
+  std::vector<const void *> letter_of_class;
+  if (!raw) {
+    letter_of_class.assign ((size_t)m->nb_class + 1, nullptr);
+    for (uint32_t k = 0; k < m->nb_class; k++)
+      letter_of_class[m->class_sorted_id[k]] = m->class_letter[k];
+  }
+  for (uint64_t i = 0; i < tail_syms; i++) {
+    const void *letter = tail + i * w;
+    if (!raw) {
+      uint32_t id;
+      memcpy (&id, letter, 4);
+      letter = id <= m->nb_class ? letter_of_class[id] : nullptr;
+      if (!letter) { /* a letter of no keyword sends every state to state 0 */
+        s = m->root;
+        continue;
+      }
+    }
+    s = acm_host_goto (s, letter);
+  }
+  return s;
+}
+
+/* ---- the scan entry point -------------------------------------------------------------------------------------------- */
+extern "C" int
+acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
+  if (!m || !scan || (!scan->text && scan->nb_symbols) || (scan->capacity && !scan->matches) || scan->lead > scan->nb_symbols)
+    return fail (ACM_B200_ERR_INVALID, "invalid argument%s", "");
+  acm_lock (m);
+  int rc = finalise_locked (m, -1);
+  if (rc) {
+    acm_unlock (m);
+    return rc;
+  }
+  acm_device_image *img = m->device;
+  const acm_tables &t = img->tab;
+  const size_t w = (size_t)t.width;
+  const ACState *from = scan->cursor && *scan->cursor ? *scan->cursor : m->root;
+  if (from->machine != m) {
+    acm_unlock (m);
+    return fail (ACM_B200_ERR_INVALID, "the cursor belongs to another machine%s", "");
+  }
+  cudaStream_t st = scan->stream ? (cudaStream_t)scan->stream : img->stream;
+  uint64_t total = 0;
+  ACMB200Stats &stats = img->stats;
+  stats.h2d_ms = stats.d2h_ms = stats.scan_kernel_ms = stats.main_kernel_ms = 0;
+  auto finish = [&] (int code) {
+    acm_unlock (m);
+    return code;
+  };
+#define TRY_LOCKED(call)                                                                            \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return finish (fail (ACM_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString (e_)));    \
+  } while (0)
+
+  if (scan->nb_symbols) {
+    ScanJob job = {};
+    job.n = scan->nb_symbols;
+    job.lead = scan->lead;
+    job.base = scan->base;
+    job.capacity = scan->capacity;
+    job.st = st;
+    /* text */
+    if (scan->text_on_device) {
+      if ((uintptr_t)scan->text & 15)
+        return finish (fail (ACM_B200_ERR_INVALID, "device text must be 16-byte aligned%s", ""));
+      job.d_text = scan->text;
+    } else {
+      if ((rc = img->d_text.ensure (scan->nb_symbols * w + 64)))
+        return finish (rc);
+      TRY_LOCKED (cudaEventRecord (img->ev[4], st));
+      TRY_LOCKED (cudaMemcpyAsync (img->d_text.ptr, scan->text, scan->nb_symbols * w, cudaMemcpyHostToDevice, st));
+      TRY_LOCKED (cudaEventRecord (img->ev[5], st));
+      job.d_text = img->d_text.ptr;
+    }
+    /* carried cursor: DFA engines start chunk 0 from its state, the filter engine sees its string as a virtual prefix */
+    if (t.engine == ACM_B200_ENGINE_FILTER) {
+      if (from->depth > 1024)
+        return finish (fail (ACM_B200_ERR_INVALID, "cursor deeper than 1024 symbols%s", ""));
+      job.prefix_len = from->depth;
+      uint32_t k = from->depth;
+      for (const ACState *s = from; s->parent; s = s->parent)
+        img->h_small->prefix[--k] = acm_symbol_of_state (m, s);
+    } else
+      job.init_dfa_state = t.dfa_of_state[from->id];
+
+    switch (t.engine) {
+      case ACM_B200_ENGINE_DFA_SMEM:
+        rc = run_dfa<uint16_t, true> (m, img, job, &total, scan->matches_on_device, scan->matches);
+        break;
+      case ACM_B200_ENGINE_DFA_GLOBAL:
+        rc = run_dfa<uint32_t, false> (m, img, job, &total, scan->matches_on_device, scan->matches);
+        break;
+      default:
+        rc = w == 1 ? run_filter<1> (m, img, job, &total, scan->matches_on_device, scan->matches)
+                    : (w == 2 ? run_filter<2> (m, img, job, &total, scan->matches_on_device, scan->matches) : run_filter<4> (m, img, job, &total, scan->matches_on_device, scan->matches));
+    }
+    if (rc)
+      return finish (rc);
+    const uint64_t got = std::min<uint64_t> (total, scan->capacity);
+    TRY_LOCKED (cudaStreamSynchronize (st));
+    float ms = 0;
+    if (!scan->text_on_device) {
+      cudaEventElapsedTime (&ms, img->ev[4], img->ev[5]);
+      stats.h2d_ms = ms;
+    }
+    cudaEventElapsedTime (&ms, img->ev[0], img->ev[3]);
+    stats.scan_kernel_ms = ms;
+    float a = 0, b = 0;
+    cudaEventElapsedTime (&a, img->ev[0], img->ev[1]);
+    if (t.engine != ACM_B200_ENGINE_FILTER)
+      cudaEventElapsedTime (&b, img->ev[2], img->ev[3]);
+    stats.main_kernel_ms = a + b;
+    if (got && !scan->matches_on_device) {
+      const auto c0 = std::chrono::steady_clock::now ();
+      TRY_LOCKED (cudaMemcpyAsync (scan->matches, job.d_matches, got * sizeof (ACMB200Match), cudaMemcpyDeviceToHost, st));
+      TRY_LOCKED (cudaStreamSynchronize (st));
+      stats.d2h_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - c0).count ();
+    }
+    /* cursor out */
+    if (scan->cursor) {
+      const uint64_t tail = std::min<uint64_t> (scan->nb_symbols, m->max_depth);
+      std::vector<unsigned char> buf (tail * w + 1);
+      const unsigned char *src = reinterpret_cast<const unsigned char *> (scan->text) + (scan->nb_symbols - tail) * w;
+      if (scan->text_on_device) {
+        TRY_LOCKED (cudaMemcpy (buf.data (), src, tail * w, cudaMemcpyDeviceToHost));
+        src = buf.data ();
+      }
+      *scan->cursor = advance_cursor (m, from, src, tail, scan->nb_symbols < m->max_depth);
+    }
+  }
+  stats.last_nb_symbols = scan->nb_symbols;
+  stats.last_nb_matches = total;
+  if (nb_matches)
+    *nb_matches = total;
+  acm_unlock (m);
+  return total > scan->capacity && scan->capacity ? ACM_B200_ERR_CAPACITY : ACM_B200_OK;
+}
+
+extern "C" int
+acm_b200_scan (ACMachine *m, const ACState **cursor, const void *text, uint64_t nb_symbols, ACMB200Match *matches, uint64_t capacity, uint64_t *nb_matches) {
+  ACMB200Scan s = {};
+  s.text = text;
+  s.nb_symbols = nb_symbols;
+  s.matches = matches;
+  s.capacity = capacity;
+  s.cursor = cursor;
+  s.sorted = 1;
+  return acm_b200_scan_ex (m, &s, nb_matches);
+}
+
+/* ---- synthetic text --------------------------------------------------------------------------------------------------- */
+extern "C" int
+acm_b200_generate_text (void *dst, int dst_on_device, uint64_t first, uint64_t nb, int kind, uint64_t seed, uint64_t plant_seed, uint64_t plant_period,
+                        const uint8_t *dict_symbols, const uint64_t *dict_offsets, uint64_t dict_nb, void *stream) {
+  if (!dst && nb)
+    return fail (ACM_B200_ERR_INVALID, "null destination%s", "");
+  GenParams g = {};
+  g.dst = reinterpret_cast<uint8_t *> (dst);
+  g.first = first;
+  g.nb = nb;
+  g.kind = kind;
+  g.seed = seed;
+  g.plant_seed = plant_seed;
+  g.plant_period = plant_period;
+  g.dict_nb = plant_period ? dict_nb : 0;
+  if (!dst_on_device) {
+    g.dict_symbols = dict_symbols;
+    g.dict_offsets = dict_offsets;
+    for (uint64_t i = 0; i < nb; i++)
+      g.dst[i] = gen_byte (g, first + i);
+    return ACM_B200_OK;
+  }
+  if (acm_b200_device_count () <= 0)
+    return fail (ACM_B200_ERR_NO_DEVICE, "no CUDA device%s", "");
+  if ((uintptr_t)dst & 15)
+    return fail (ACM_B200_ERR_INVALID, "device destination must be 16-byte aligned%s", "");
+  cudaStream_t st = (cudaStream_t)stream;
+  void *d_sym = nullptr, *d_off = nullptr;
+  if (g.dict_nb) {
+    const size_t sym_bytes = dict_offsets[dict_nb], off_bytes = (dict_nb + 1) * 8;
+    CUDA_TRY (cudaMalloc (&d_sym, sym_bytes ? sym_bytes : 1));
+    CUDA_TRY (cudaMalloc (&d_off, off_bytes));
+    CUDA_TRY (cudaMemcpyAsync (d_sym, dict_symbols, sym_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY (cudaMemcpyAsync (d_off, dict_offsets, off_bytes, cudaMemcpyHostToDevice, st));
+    g.dict_symbols = reinterpret_cast<const uint8_t *> (d_sym);
+    g.dict_offsets = reinterpret_cast<const uint64_t *> (d_off);
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, 0);
+  generate_text_kernel<<<sms * 8, 256, 0, st>>> (g);
+  CUDA_TRY (cudaGetLastError ());
+  CUDA_TRY (cudaStreamSynchronize (st));
+  if (d_sym)
+    cudaFree (d_sym);
+  if (d_off)
+    cudaFree (d_off);
+  return ACM_B200_OK;
+}

@@ -1,0 +1,448 @@
+/* acm_finalise.c -- compiles the host trie (goto / fail / outputs) into the flat images the GPU scans.
+ *
+ * Role of the reference's Algorithm 3 pass (aho_corasick.c:386-417) plus everything the reference leaves in pointer form:
+ *   symbol remap     device symbols are raw letters for ACM_CMP_DEFAULT with 1/2/4-byte letters, else stable class ids
+ *                    assigned with the user's comparator (symbol identity is cmp()==0, aho_corasick.c:102,299);
+ *   DFA engines      states renumbered by (has outputs, depth); delta[s][class] = child, else delta[f(s)][class]
+ *                    (Appendix C rules 1-2), filled in depth order so f(s)'s row is final; CSR output sets list the
+ *                    keyword states along s, f(s), ... longest first (rule 4) with length = depth (rule 5);
+ *   filter engine    the last q symbols of every keyword feed a blocked Bloom filter (shared memory) and an exact q-gram
+ *                    hash table; a reverse trie (keywords read right to left) in a hash table verifies candidates.
+ * Engine choice and sizes are in DESIGN.md.
+ */
+#include "acm_internal.h"
+#include "acm_tables.h"
+#include <stdlib.h>
+#include <string.h>
+
+uint32_t
+acm_symbol_of_state (const struct _ac_machine *m, const struct _ac_state *s) {
+  switch (m->symbol_kind) {
+    case ACM_SYM_RAW1:
+      return *(const uint8_t *)s->letter;
+    case ACM_SYM_RAW2: {
+      uint16_t v;
+      memcpy (&v, s->letter, 2);
+      return v;
+    }
+    case ACM_SYM_RAW4: {
+      uint32_t v;
+      memcpy (&v, s->letter, 4);
+      return v;
+    }
+    default:
+      return m->class_of_state[s->id];
+  }
+}
+
+/* ---- class ids for user comparators -------------------------------------------------------------------------------- */
+static int64_t
+class_slot (const struct _ac_machine *m, const void *letter) {
+  uint32_t lo = 0, hi = m->nb_class;
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    int c = m->cmp (letter, m->class_letter[mid], m->cmp_arg);
+    if (c == 0)
+      return mid;
+    if (c < 0)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return ~(int64_t)lo;
+}
+
+static int
+extend_classes (struct _ac_machine *m) {
+  if (m->cap_class_states < m->nb_states) {
+    size_t cap = m->nb_states + m->nb_states / 2 + 16;
+    uint32_t *grown = realloc (m->class_of_state, cap * sizeof (*grown));
+    if (!grown)
+      return ACM_B200_ERR_NOMEM;
+    m->class_of_state = grown;
+    m->cap_class_states = cap;
+  }
+  size_t id = 0;
+  for (struct acm_state_block *b = m->blocks; b; b = b->next)
+    for (uint32_t i = 0; i < b->used; i++, id++) {
+      if (id < m->class_states_done)
+        continue;
+      struct _ac_state *s = &b->states[i];
+      if (!s->parent) {
+        m->class_of_state[id] = 0;
+        continue;
+      }
+      int64_t k = class_slot (m, s->letter);
+      if (k < 0) {
+        if (m->nb_class == m->cap_class) {
+          uint32_t cap = m->cap_class ? m->cap_class * 2 : 64;
+          const void **gl = realloc (m->class_letter, cap * sizeof (*gl));
+          uint32_t *gi = realloc (m->class_sorted_id, cap * sizeof (*gi));
+          if (gl)
+            m->class_letter = gl;
+          if (gi)
+            m->class_sorted_id = gi;
+          if (!gl || !gi)
+            return ACM_B200_ERR_NOMEM;
+          m->cap_class = cap;
+        }
+        uint32_t at = (uint32_t)~k;
+        memmove (m->class_letter + at + 1, m->class_letter + at, (m->nb_class - at) * sizeof (*m->class_letter));
+        memmove (m->class_sorted_id + at + 1, m->class_sorted_id + at, (m->nb_class - at) * sizeof (*m->class_sorted_id));
+        m->class_letter[at] = s->letter;
+        m->class_sorted_id[at] = ++m->nb_class; /* ids start at 1 */
+        k = at;
+      }
+      m->class_of_state[id] = m->class_sorted_id[k];
+    }
+  m->class_states_done = m->nb_states;
+  return ACM_B200_OK;
+}
+
+int
+acm_b200_remap_text (ACMachine *m, const void *letters, size_t letter_size, uint64_t nb, uint32_t *class_ids) {
+  if (!m || (!letters && nb) || !class_ids || !letter_size)
+    return ACM_B200_ERR_INVALID;
+  if (m->symbol_kind == ACM_SYM_RAW1 || m->symbol_kind == ACM_SYM_RAW2 || m->symbol_kind == ACM_SYM_RAW4) {
+    /* raw machines need no remap; give the identity so callers can be generic */
+    for (uint64_t i = 0; i < nb; i++) {
+      uint32_t v = 0;
+      memcpy (&v, (const char *)letters + i * letter_size, letter_size < 4 ? letter_size : 4);
+      class_ids[i] = v;
+    }
+    return ACM_B200_OK;
+  }
+  acm_lock (m);
+  int rc = extend_classes (m);
+  if (rc == ACM_B200_OK)
+    for (uint64_t i = 0; i < nb; i++) {
+      int64_t k = class_slot (m, (const char *)letters + i * letter_size);
+      class_ids[i] = k >= 0 ? m->class_sorted_id[k] : 0;
+    }
+  acm_unlock (m);
+  return rc;
+}
+
+/* ---- helpers -------------------------------------------------------------------------------------------------------- */
+static uint64_t
+pow2_at_least (uint64_t x) {
+  uint64_t p = 1;
+  while (p < x)
+    p <<= 1;
+  return p;
+}
+
+static void
+slot_insert (acm_slot *tab, uint64_t nslots, uint64_t key, uint32_t node, uint32_t keyword) {
+  uint64_t j = acm_mix64 (key) & (nslots - 1);
+  while (tab[j].node != ACM_TAB_NONE)
+    j = (j + 1) & (nslots - 1);
+  tab[j] = (acm_slot){ key, node, keyword };
+}
+
+static acm_slot *
+slot_find (acm_slot *tab, uint64_t nslots, uint64_t key) {
+  uint64_t j = acm_mix64 (key) & (nslots - 1);
+  while (tab[j].node != ACM_TAB_NONE) {
+    if (tab[j].key == key)
+      return &tab[j];
+    j = (j + 1) & (nslots - 1);
+  }
+  return 0;
+}
+
+void
+acm_free_tables (struct acm_tables *t) {
+  free (t->delta);
+  free (t->out_offsets);
+  free (t->out_entries);
+  free (t->dfa_of_state);
+  free (t->bloom);
+  free (t->qgrams);
+  free (t->edges);
+  memset (t, 0, sizeof (*t));
+}
+
+/* ---- DFA engines ---------------------------------------------------------------------------------------------------- */
+static int
+build_dfa (struct _ac_machine *m, struct acm_tables *t, struct _ac_state **by_depth) {
+  const uint32_t n = (uint32_t)m->nb_states, K = t->nb_classes;
+  /* renumber: states without outputs first (depth order, state 0 -> 0), then states with outputs */
+  t->dfa_of_state = malloc ((size_t)n * sizeof (uint32_t));
+  if (!t->dfa_of_state)
+    return ACM_B200_ERR_NOMEM;
+  uint32_t next = 0;
+  for (uint32_t i = 0; i < n; i++)
+    if (!by_depth[i]->nb_outputs)
+      t->dfa_of_state[by_depth[i]->id] = next++;
+  t->out_threshold = next;
+  for (uint32_t i = 0; i < n; i++)
+    if (by_depth[i]->nb_outputs)
+      t->dfa_of_state[by_depth[i]->id] = next++;
+  t->nb_dfa_states = n;
+
+  t->delta_bytes = (size_t)n * K * (size_t)t->delta_entry_bytes;
+  t->delta = malloc (t->delta_bytes ? t->delta_bytes : 1);
+  if (!t->delta)
+    return ACM_B200_ERR_NOMEM;
+  uint16_t *d16 = t->delta_entry_bytes == 2 ? t->delta : 0;
+  uint32_t *d32 = t->delta_entry_bytes == 4 ? t->delta : 0;
+  for (uint32_t i = 0; i < n; i++) { /* depth order: the row of f(s) is final before the row of s */
+    const struct _ac_state *s = by_depth[i];
+    size_t row = (size_t)t->dfa_of_state[s->id] * K;
+    if (!s->parent) {
+      if (d16)
+        memset (d16 + row, 0, K * 2);
+      else
+        memset (d32 + row, 0, (size_t)K * 4);
+    } else {
+      size_t frow = (size_t)t->dfa_of_state[s->fail->id] * K;
+      if (d16)
+        memcpy (d16 + row, d16 + frow, K * 2);
+      else
+        memcpy (d32 + row, d32 + frow, (size_t)K * 4);
+    }
+    for (uint32_t k = 0; k < s->nb_children; k++) {
+      const struct _ac_state *c = s->children[k];
+      uint32_t cls = t->class_of_byte[*(const uint8_t *)c->letter], to = t->dfa_of_state[c->id];
+      if (d16)
+        d16[row + cls] = (uint16_t)to;
+      else
+        d32[row + cls] = to;
+    }
+  }
+  /* CSR output sets */
+  uint32_t nout = n - t->out_threshold;
+  t->out_offsets = malloc (((size_t)nout + 1) * sizeof (uint32_t));
+  if (!t->out_offsets)
+    return ACM_B200_ERR_NOMEM;
+  struct _ac_state **of_dfa = malloc (((size_t)nout + 1) * sizeof (*of_dfa));
+  if (!of_dfa)
+    return ACM_B200_ERR_NOMEM;
+  for (uint32_t i = 0; i < n; i++)
+    if (by_depth[i]->nb_outputs)
+      of_dfa[t->dfa_of_state[by_depth[i]->id] - t->out_threshold] = by_depth[i];
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < nout; i++) {
+    t->out_offsets[i] = (uint32_t)total;
+    total += of_dfa[i]->nb_outputs;
+  }
+  if (total > 0xFFFFFFFFull) {
+    free (of_dfa);
+    return ACM_B200_ERR_NOMEM;
+  }
+  t->out_offsets[nout] = (uint32_t)total;
+  t->nb_out_entries = total;
+  t->out_entries = malloc ((total ? total : 1) * sizeof (acm_output));
+  if (!t->out_entries) {
+    free (of_dfa);
+    return ACM_B200_ERR_NOMEM;
+  }
+  for (uint32_t i = 0; i < nout; i++) {
+    acm_output *o = t->out_entries + t->out_offsets[i];
+    size_t left = of_dfa[i]->nb_outputs;
+    for (const struct _ac_state *s = of_dfa[i]; left; s = s->fail)
+      if (s->rank != ACM_NONE) {
+        *o++ = (acm_output){ s->rank, s->depth };
+        left--;
+      }
+  }
+  free (of_dfa);
+  return ACM_B200_OK;
+}
+
+/* ---- filter engine -------------------------------------------------------------------------------------------------- */
+static int
+build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget) {
+  const uint32_t nk = (uint32_t)m->nb_sequences;
+  uint64_t total_syms = 0;
+  for (uint32_t r = 0; r < nk; r++)
+    total_syms += m->keywords[r]->depth;
+  t->q = m->lmin == ACM_NONE ? 1 : m->lmin;
+  uint32_t qmax = t->width == 1 ? 4 : 2;
+  if (t->q > qmax)
+    t->q = qmax;
+  /* reverse trie in an edge hash table; node 0 = root */
+  t->edge_slots = pow2_at_least (2 * total_syms + 16);
+  t->edges = malloc (t->edge_slots * sizeof (acm_slot));
+  if (!t->edges)
+    return ACM_B200_ERR_NOMEM;
+  memset (t->edges, 0xFF, t->edge_slots * sizeof (acm_slot));
+  uint32_t nodes = 1;
+  uint64_t nq = 0; /* distinct depth-q nodes */
+  /* first pass: build nodes; remember, for every depth-q node, its packed key */
+  uint64_t cap_q = 1024;
+  uint64_t *qkeys = malloc (cap_q * sizeof (*qkeys));
+  uint32_t *qnodes = malloc (cap_q * sizeof (*qnodes));
+  if (!qkeys || !qnodes)
+    return ACM_B200_ERR_NOMEM;
+  const int shift = t->width == 1 ? 8 : (t->width == 2 ? 16 : 32);
+  for (uint32_t r = 0; r < nk; r++) {
+    uint32_t node = 0, depth = 0;
+    uint64_t key = 0;
+    for (const struct _ac_state *s = m->keywords[r]; s->parent; s = s->parent) { /* last letter first */
+      uint32_t sym = acm_symbol_of_state (m, s);
+      uint64_t ekey = ((uint64_t)node << 32) | sym;
+      acm_slot *e = slot_find (t->edges, t->edge_slots, ekey);
+      int created = 0;
+      if (!e) {
+        slot_insert (t->edges, t->edge_slots, ekey, nodes++, ACM_TAB_NONE);
+        e = slot_find (t->edges, t->edge_slots, ekey);
+        created = 1;
+      }
+      node = e->node;
+      depth++;
+      if (depth <= t->q) {
+        key = shift == 32 ? ((depth == 1 ? 0 : key << 32) | sym) : ((key << shift) | sym);
+        if (depth == t->q && created) {
+          if (nq == cap_q) {
+            cap_q *= 2;
+            qkeys = realloc (qkeys, cap_q * sizeof (*qkeys));
+            qnodes = realloc (qnodes, cap_q * sizeof (*qnodes));
+            if (!qkeys || !qnodes)
+              return ACM_B200_ERR_NOMEM;
+          }
+          qkeys[nq] = key;
+          qnodes[nq++] = node;
+        }
+      }
+      if (!s->parent->parent) /* s is the first letter of the keyword: the reversed keyword ends at `node` */
+        e->keyword = r;
+    }
+  }
+  t->nb_rev_nodes = nodes;
+  /* exact q-gram table; the keyword field tells whether a keyword of exactly q symbols ends at that node */
+  t->qgram_slots = pow2_at_least (2 * nq + 16);
+  t->qgrams = malloc (t->qgram_slots * sizeof (acm_slot));
+  if (!t->qgrams)
+    return ACM_B200_ERR_NOMEM;
+  memset (t->qgrams, 0xFF, t->qgram_slots * sizeof (acm_slot));
+  /* node -> keyword for depth-q nodes: look the edge up again through the keyword walk (cheap: reuse edge slots) */
+  for (uint64_t i = 0; i < nq; i++)
+    slot_insert (t->qgrams, t->qgram_slots, qkeys[i], qnodes[i], ACM_TAB_NONE);
+  for (uint32_t r = 0; r < nk; r++)
+    if (m->keywords[r]->depth == t->q) { /* keyword of exactly q symbols */
+      uint64_t key = 0;
+      uint32_t depth = 0;
+      for (const struct _ac_state *s = m->keywords[r]; s->parent; s = s->parent) {
+        uint32_t sym = acm_symbol_of_state (m, s);
+        depth++;
+        key = shift == 32 ? ((depth == 1 ? 0 : key << 32) | sym) : ((key << shift) | sym);
+      }
+      slot_find (t->qgrams, t->qgram_slots, key)->keyword = r;
+    }
+  /* blocked Bloom filter sized to the shared-memory budget: ~24 bits per q-gram, at most the budget */
+  uint64_t want_words = m->option_bloom_words ? m->option_bloom_words : pow2_at_least ((nq * 24 + 31) / 32);
+  uint64_t max_words = smem_budget / 4;
+  if (want_words > max_words)
+    want_words = max_words;
+  if (want_words < 64)
+    want_words = 64;
+  t->bloom_words = (uint32_t)want_words;
+  t->bloom_k = m->option_bloom_k ? (uint32_t)m->option_bloom_k : 2;
+  if (t->bloom_k > 3)
+    t->bloom_k = 3;
+  t->bloom = calloc (t->bloom_words, sizeof (uint32_t));
+  if (!t->bloom)
+    return ACM_B200_ERR_NOMEM;
+  for (uint64_t i = 0; i < nq; i++) {
+    uint32_t f = acm_fold_key (qkeys[i]);
+    t->bloom[acm_bloom_word (f, t->bloom_words)] |= acm_bloom_mask (f, t->bloom_k);
+  }
+  free (qkeys);
+  free (qnodes);
+  return ACM_B200_OK;
+}
+
+/* ---- entry ---------------------------------------------------------------------------------------------------------- */
+int
+acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget) {
+  memset (t, 0, sizeof (*t));
+  const uint32_t n = (uint32_t)m->nb_states;
+  t->nb_states = n;
+  t->nb_keywords = (uint32_t)m->nb_sequences;
+  t->lmax = m->lmax;
+  t->lmin = m->lmin == ACM_NONE ? 0 : m->lmin;
+  const int raw = m->symbol_kind == ACM_SYM_RAW1 || m->symbol_kind == ACM_SYM_RAW2 || m->symbol_kind == ACM_SYM_RAW4;
+  t->width = raw ? (int)m->symbol_size : 4;
+  if (!raw) {
+    int rc = extend_classes (m);
+    if (rc)
+      return rc;
+  }
+  /* byte classes (DFA engines) */
+  uint32_t K = 1;
+  if (t->width == 1) {
+    int used[256] = { 0 };
+    for (struct acm_state_block *b = m->blocks; b; b = b->next)
+      for (uint32_t i = 0; i < b->used; i++)
+        if (b->states[i].parent)
+          used[*(const uint8_t *)b->states[i].letter] = 1;
+    for (int c = 0; c < 256; c++)
+      t->class_of_byte[c] = used[c] ? (uint8_t)K++ : 0;
+    if (K > 255) { /* all 256 byte values used: no room for an "other" class, none needed */
+      K = 256;
+      for (int c = 0; c < 256; c++)
+        t->class_of_byte[c] = (uint8_t)c;
+    }
+  }
+  t->nb_classes = K;
+
+  /* engine choice */
+  int engine = ACM_B200_ENGINE_AUTO;
+  if (!strcmp (m->engine_override, "dfa_smem"))
+    engine = ACM_B200_ENGINE_DFA_SMEM;
+  else if (!strcmp (m->engine_override, "dfa_global"))
+    engine = ACM_B200_ENGINE_DFA_GLOBAL;
+  else if (!strcmp (m->engine_override, "filter"))
+    engine = ACM_B200_ENGINE_FILTER;
+  const uint64_t smem_table = (uint64_t)n * K * 2;
+  const int smem_ok = t->width == 1 && n <= 0xFFFF && smem_table + 1024 <= smem_budget;
+  const int global_ok = t->width == 1 && (uint64_t)n * K * 4 <= (8ull << 30);
+  if (engine == ACM_B200_ENGINE_DFA_SMEM && !smem_ok)
+    engine = ACM_B200_ENGINE_AUTO;
+  if (engine == ACM_B200_ENGINE_DFA_GLOBAL && !global_ok)
+    engine = ACM_B200_ENGINE_AUTO;
+  if (engine == ACM_B200_ENGINE_AUTO) {
+    if (smem_ok)
+      engine = ACM_B200_ENGINE_DFA_SMEM;
+    else if (t->width == 1 && t->lmin < 3 && global_ok)
+      engine = ACM_B200_ENGINE_DFA_GLOBAL; /* short keywords: a suffix filter would let most positions through */
+    else
+      engine = ACM_B200_ENGINE_FILTER;
+  }
+  if (t->nb_keywords == 0 && t->width != 1)
+    engine = ACM_B200_ENGINE_FILTER;
+  t->engine = engine;
+
+  int rc;
+  if (engine == ACM_B200_ENGINE_FILTER)
+    rc = build_filter (m, t, smem_budget);
+  else {
+    t->delta_entry_bytes = engine == ACM_B200_ENGINE_DFA_SMEM ? 2 : 4;
+    /* states sorted by depth (counting sort) */
+    uint32_t maxd = 0;
+    for (struct acm_state_block *b = m->blocks; b; b = b->next)
+      for (uint32_t i = 0; i < b->used; i++)
+        if (b->states[i].depth > maxd)
+          maxd = b->states[i].depth;
+    uint32_t *start = calloc ((size_t)maxd + 2, sizeof (uint32_t));
+    struct _ac_state **by_depth = malloc ((size_t)n * sizeof (*by_depth));
+    if (!start || !by_depth)
+      return ACM_B200_ERR_NOMEM;
+    for (struct acm_state_block *b = m->blocks; b; b = b->next)
+      for (uint32_t i = 0; i < b->used; i++)
+        start[b->states[i].depth + 1]++;
+    for (uint32_t d = 0; d <= maxd; d++)
+      start[d + 1] += start[d];
+    for (struct acm_state_block *b = m->blocks; b; b = b->next)
+      for (uint32_t i = 0; i < b->used; i++)
+        by_depth[start[b->states[i].depth]++] = &b->states[i];
+    rc = build_dfa (m, t, by_depth);
+    free (start);
+    free (by_depth);
+  }
+  if (rc)
+    acm_free_tables (t);
+  return rc;
+}

@@ -1,0 +1,590 @@
+/* acm_kernels.cuh -- the sm_100a kernels of the scan path.  Included by acm_device.cu only.
+ *
+ * Two engine families, both exact:
+ *
+ *  DFA engines (byte alphabets).  The text is cut into per-thread chunks; every thread first re-reads the
+ *  (max keyword length - 1) symbols before its chunk from state 0 and then walks its chunk through the dense delta table
+ *  (one class lookup + one delta lookup per byte).  Pass 1 counts the occurrences of every chunk, a device scan turns the
+ *  counts into offsets, pass 2 re-walks and writes the records in place -- so the output is in the reference's emission order
+ *  without any sort.  delta lives in shared memory (uint16 entries) or in global memory (uint32 entries, L2 resident).
+ *
+ *  Filter engine (any alphabet).  A keyword can only END at position p if the q symbols ending at p are the last q symbols
+ *  of some keyword (q = min(shortest keyword, 4 bytes / 2 wider symbols)).  Kernel F1 streams the text with coalesced 16-byte
+ *  loads, tests every position against a blocked Bloom filter in shared memory (one 32-bit shared load per position), confirms
+ *  the survivors in an exact q-gram hash table (L2) and appends the confirmed positions of each warp tile, in position order,
+ *  to a candidate list (ballot/popc compaction).  F2 walks the reverse trie leftwards from every candidate and counts, a device
+ *  scan gives offsets, F4 walks again and writes the records, longest keyword first.
+ */
+#pragma once
+#include "acm_tables.h"
+#include "acm_b200.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acm {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Device-wide exclusive scan of uint32 counts into uint64 offsets (three small kernels; the data is a few MB at most). */
+/* ------------------------------------------------------------------------------------------------------------------ */
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4; /* per thread */
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t
+block_exclusive_scan (uint64_t v, uint64_t *total, uint64_t *warp_sums /* [32] shared */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = __shfl_up_sync (kFull, incl, d);
+    if (lane >= d)
+      incl += o;
+  }
+  if (lane == 31)
+    warp_sums[warp] = incl;
+  __syncthreads ();
+  if (warp == 0) {
+    uint64_t w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0, wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t o = __shfl_up_sync (kFull, wi, d);
+      if (lane >= d)
+        wi += o;
+    }
+    warp_sums[lane] = wi - w; /* exclusive */
+    if (lane == 31)
+      *total = wi;
+  }
+  __syncthreads ();
+  uint64_t r = warp_sums[warp] + incl - v;
+  __syncthreads ();
+  return r;
+}
+
+__global__ void __launch_bounds__ (kScanThreads)
+scan_block_sums_kernel (const uint32_t *__restrict__ counts, uint64_t n, uint64_t *__restrict__ block_sums) {
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t total;
+  uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems, v = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++)
+    if (base + i < n)
+      v += counts[base + i];
+  block_exclusive_scan (v, &total, warp_sums);
+  if (threadIdx.x == 0)
+    block_sums[blockIdx.x] = total;
+}
+
+/* one block: exclusive scan of the block sums in place, grand total to *grand */
+__global__ void __launch_bounds__ (kScanThreads)
+scan_spine_kernel (uint64_t *__restrict__ block_sums, uint64_t nblocks, uint64_t *__restrict__ grand) {
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t total;
+  uint64_t carry = 0;
+  for (uint64_t start = 0; start < nblocks; start += kScanThreads) {
+    uint64_t i = start + threadIdx.x, v = i < nblocks ? block_sums[i] : 0;
+    uint64_t ex = block_exclusive_scan (v, &total, warp_sums);
+    if (i < nblocks)
+      block_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads ();
+  }
+  if (threadIdx.x == 0)
+    *grand = carry;
+}
+
+__global__ void __launch_bounds__ (kScanThreads)
+scan_apply_kernel (const uint32_t *__restrict__ counts, uint64_t n, const uint64_t *__restrict__ block_sums, uint64_t *__restrict__ offsets) {
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t total;
+  uint64_t base = (uint64_t)blockIdx.x * kScanBlock + (uint64_t)threadIdx.x * kScanItems, v = 0;
+  uint32_t c[kScanItems];
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    c[i] = base + i < n ? counts[base + i] : 0;
+    v += c[i];
+  }
+  uint64_t ex = block_exclusive_scan (v, &total, warp_sums) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; i++) {
+    if (base + i < n)
+      offsets[base + i] = ex;
+    ex += c[i];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* DFA engines                                                                                                         */
+/* ------------------------------------------------------------------------------------------------------------------ */
+struct DfaParams {
+  const uint8_t *text;
+  uint64_t n;     /* symbols */
+  uint64_t lead;  /* occurrences ending before `lead` are not reported */
+  uint64_t base;  /* added to reported end positions */
+  uint64_t chunk; /* symbols per chunk, multiple of 16 */
+  uint64_t nchunks;
+  uint32_t warm;       /* symbols re-read before a chunk = max keyword length - 1 */
+  uint32_t init_state; /* dfa state chunk 0 starts from (carried cursor) */
+  const void *delta;   /* [nb_states][K] */
+  uint32_t K, nb_states, out_threshold;
+  const uint32_t *out_offsets;
+  const acm_output *out_entries;
+  uint32_t *chunk_counts;        /* pass 1 out */
+  const uint64_t *chunk_offsets; /* pass 2 in */
+  ACMB200Match *matches;
+  uint64_t capacity;
+  uint8_t class_of_byte[256];
+};
+
+template <typename Entry, bool kShared, bool kEmit>
+__global__ void __launch_bounds__ (kShared ? 1024 : 256)
+dfa_scan_kernel (const __grid_constant__ DfaParams p) {
+  extern __shared__ __align__ (16) unsigned char smem[];
+  uint8_t *s_class = smem;
+  Entry *s_delta = reinterpret_cast<Entry *> (smem + 256);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_class[i] = p.class_of_byte[i];
+  if (kShared) {
+    /* table bytes rounded up to 16 by the host */
+    const uint4 *src = reinterpret_cast<const uint4 *> (p.delta);
+    uint4 *dst = reinterpret_cast<uint4 *> (s_delta);
+    const uint32_t vecs = (uint32_t)(((uint64_t)p.nb_states * p.K * sizeof (Entry) + 15) / 16);
+    for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads ();
+  const Entry *__restrict__ delta = kShared ? s_delta : reinterpret_cast<const Entry *> (p.delta);
+  const uint32_t K = p.K, thr = p.out_threshold;
+
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t start = c * p.chunk;
+    const uint64_t end = min (p.n, start + p.chunk);
+    const uint64_t report_from = max (start, p.lead);
+    /* chunks that start within `warm` symbols of the text start re-read from symbol 0, where the true state is the carried one */
+    const bool from_origin = start <= p.warm;
+    uint32_t state = from_origin ? p.init_state : 0;
+    uint64_t pos = from_origin ? 0 : (start - p.warm) & ~(uint64_t)15;
+    uint32_t count = 0;
+    uint64_t out = kEmit ? p.chunk_offsets[c] : 0;
+
+    auto step = [&] (uint32_t byte, uint64_t at) {
+      state = delta[state * K + s_class[byte]];
+      if (state >= thr && at >= report_from) {
+        const uint32_t o = state - thr, lo = p.out_offsets[o], hi = p.out_offsets[o + 1];
+        if (kEmit) {
+          for (uint32_t j = lo; j < hi; j++, out++)
+            if (out < p.capacity) {
+              const acm_output e = p.out_entries[j];
+              p.matches[out] = ACMB200Match{ p.base + at, e.keyword, e.length };
+            }
+        } else
+          count += hi - lo;
+      }
+    };
+    /* warm-up + chunk, 16 bytes at a time while a whole vector is inside the text */
+    while (pos + 16 <= end) {
+      const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
+      const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, pos + i);
+      pos += 16;
+    }
+    for (; pos < end; pos++)
+      step (p.text[pos], pos);
+    if (!kEmit)
+      p.chunk_counts[c] = count;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Filter engine                                                                                                       */
+/* ------------------------------------------------------------------------------------------------------------------ */
+struct FilterParams {
+  const void *text;
+  uint64_t n, lead, base;
+  uint32_t q;
+  uint32_t tile_rows;  /* 512-byte rows per warp tile */
+  uint32_t tile_syms;  /* symbols per tile */
+  uint64_t ntiles;
+  const uint32_t *bloom;
+  uint32_t bloom_words, bloom_k;
+  const acm_slot *qgrams;
+  uint64_t qgram_mask;
+  const acm_slot *edges;
+  uint64_t edge_mask;
+  const uint32_t *prefix; /* symbols virtually preceding the text (carried cursor), prefix_len of them */
+  uint32_t prefix_len;
+  uint32_t stage_cap; /* raw hits a warp can stage per tile */
+  /* F1 out */
+  uint64_t *cand_pos;
+  uint64_t cand_cap;
+  unsigned long long *cand_count;
+  uint64_t *tile_first;
+  uint32_t *tile_n;
+  uint32_t *overflow;
+  /* F2 out / F4 in */
+  uint32_t *cand_matches;
+  uint32_t *tile_matches;
+  const uint64_t *tile_offsets;
+  ACMB200Match *matches;
+  uint64_t capacity;
+};
+
+template <int W> struct SymT;
+template <> struct SymT<1> { typedef uint8_t type; };
+template <> struct SymT<2> { typedef uint16_t type; };
+template <> struct SymT<4> { typedef uint32_t type; };
+
+/* symbol at (possibly negative) position: the carried-cursor prefix sits virtually before the text */
+template <int W>
+__device__ __forceinline__ bool
+symbol_at (const FilterParams &p, int64_t pos, uint32_t *sym) {
+  if (pos >= 0) {
+    *sym = reinterpret_cast<const typename SymT<W>::type *> (p.text)[pos];
+    return true;
+  }
+  if (pos >= -(int64_t)p.prefix_len) {
+    *sym = p.prefix[(int64_t)p.prefix_len + pos];
+    return true;
+  }
+  return false;
+}
+
+/* packed key of the q symbols ending at pos (last symbol most significant), false if they do not all exist */
+template <int W>
+__device__ __forceinline__ bool
+qgram_key_at (const FilterParams &p, int64_t pos, uint64_t *key) {
+  uint64_t k = 0;
+  for (uint32_t j = 0; j < p.q; j++) {
+    uint32_t s;
+    if (!symbol_at<W> (p, pos - j, &s))
+      return false;
+    k = W == 4 ? ((j == 0 ? 0 : k << 32) | s) : ((k << (8 * W)) | s);
+  }
+  *key = k;
+  return true;
+}
+
+__device__ __forceinline__ bool
+slot_lookup (const acm_slot *__restrict__ tab, uint64_t mask, uint64_t key, uint32_t *node, uint32_t *keyword) {
+  uint64_t j = acm_mix64 (key) & mask;
+  for (;;) {
+    const uint4 raw = __ldg (reinterpret_cast<const uint4 *> (tab + j));
+    if (raw.z == ACM_TAB_NONE)
+      return false;
+    if ((((uint64_t)raw.y << 32) | raw.x) == key) {
+      *node = raw.z;
+      *keyword = raw.w;
+      return true;
+    }
+    j = (j + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ bool
+bloom_test (const uint32_t *s_bloom, uint32_t folded, uint32_t nwords, uint32_t k) {
+  const uint32_t word = s_bloom[acm_bloom_word (folded, nwords)];
+  const uint32_t g = folded * ACM_BLOOM_C2;
+  uint32_t t = word >> (g >> 27);
+  if (k > 1)
+    t &= word >> ((g >> 22) & 31u);
+  if (k > 2)
+    t &= word >> ((g >> 17) & 31u);
+  return t & 1u;
+}
+
+/* F1.  One warp per tile of tile_rows x 512 bytes; lane l of row r owns the 16 bytes at r*512 + l*16. */
+template <int W, int kRows>
+__global__ void __launch_bounds__ (1024, 1)
+filter_scan_kernel (const __grid_constant__ FilterParams p) {
+  extern __shared__ __align__ (16) unsigned char smem[];
+  uint32_t *s_bloom = reinterpret_cast<uint32_t *> (smem);
+  uint16_t *s_stage_all = reinterpret_cast<uint16_t *> (smem + (size_t)p.bloom_words * 4);
+  for (uint32_t i = threadIdx.x; i < p.bloom_words; i += blockDim.x)
+    s_bloom[i] = p.bloom[i];
+  __syncthreads ();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  uint16_t *stage = s_stage_all + (size_t)warp * p.stage_cap;
+  constexpr int kSyms = 16 / W;          /* symbols per lane per row */
+  constexpr int kRowSyms = 32 * kSyms;   /* symbols per row */
+  const uint32_t q = p.q, nwords = p.bloom_words, bk = p.bloom_k;
+  const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
+  const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
+
+  for (uint64_t tile = (uint64_t)blockIdx.x * warps + warp; tile < p.ntiles; tile += (uint64_t)gridDim.x * warps) {
+    const uint64_t tile_base = tile * p.tile_syms; /* in symbols */
+    uint32_t staged = 0;                           /* warp-uniform */
+
+    /* positions whose window reaches into the carried-cursor prefix: checked exactly, by lane 0 of the first tile */
+    if (tile == 0 && p.prefix_len && q > 1) {
+      if (lane == 0)
+        for (uint64_t pos = p.lead; pos < min ((uint64_t)(q - 1), p.n); pos++) {
+          uint64_t key;
+          if (qgram_key_at<W> (p, (int64_t)pos, &key) && staged < p.stage_cap)
+            stage[staged++] = (uint16_t)pos; /* confirmed again below like any other staged hit */
+        }
+      staged = __shfl_sync (kFull, staged, 0);
+    }
+
+    /* all rows of the tile are requested up front: kRows independent 16-byte loads per lane in flight */
+    uint4 v[kRows];
+    uint32_t prev[kRows]; /* the 4 bytes before the lane's 16 */
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+      const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
+      if ((pos0 + kSyms) <= p.n)
+        v[r] = *reinterpret_cast<const uint4 *> (text8 + pos0 * W);
+      else {
+        uint32_t w[4] = { 0, 0, 0, 0 };
+        for (int i = 0; i < 16; i++)
+          if (pos0 * W + i < p.n * W)
+            w[i >> 2] |= (uint32_t)text8[pos0 * W + i] << (8 * (i & 3));
+        v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+      uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
+      if (lane == 0) {
+        if (r > 0)
+          up = 0; /* fixed below from the previous row's lane 31 */
+        else {
+          const uint64_t b0 = tile_base * W;
+          up = b0 >= 4 ? *reinterpret_cast<const uint32_t *> (text8 + b0 - 4) : 0;
+        }
+      }
+      prev[r] = up;
+    }
+#pragma unroll
+    for (int r = 1; r < kRows; r++) {
+      const uint32_t last = __shfl_sync (kFull, v[r - 1].w, 31);
+      if (lane == 0)
+        prev[r] = last;
+    }
+
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+      const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
+      const uint32_t w[5] = { prev[r], v[r].x, v[r].y, v[r].z, v[r].w };
+      uint32_t hits = 0;
+      if (W == 1) {
+        const uint32_t drop = 8u * (4u - q);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          /* the 4 bytes ending at byte i: b[i-3..i], b[i] most significant */
+          const int j = (i >> 2) + 1, sh = ((i & 3) + 1) * 8;
+          const uint32_t win = sh == 32 ? w[j] : __funnelshift_r (w[j - 1], w[j], sh);
+          if (bloom_test (s_bloom, win >> drop, nwords, bk))
+            hits |= 1u << i;
+        }
+      } else if (W == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          /* symbols s[i-1], s[i]: 32 bits ending at halfword i */
+          const int j = (i >> 1) + 1;
+          const uint32_t pair = (i & 1) ? w[j] : __funnelshift_r (w[j - 1], w[j], 16); /* low half = s[i-1], high half = s[i] */
+          const uint32_t key = q == 2 ? pair : (pair >> 16);
+          if (bloom_test (s_bloom, key, nwords, bk))
+            hits |= 1u << i;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint64_t key = q == 2 ? (((uint64_t)w[i + 1] << 32) | w[i]) : (uint64_t)w[i + 1];
+          if (bloom_test (s_bloom, acm_fold_key (key), nwords, bk))
+            hits |= 1u << i;
+        }
+      }
+      /* drop positions outside [first_valid, n) */
+      if (pos0 < first_valid || pos0 + kSyms > p.n) {
+        uint32_t keep = 0;
+        for (int i = 0; i < kSyms; i++)
+          if (pos0 + i >= first_valid && pos0 + i < p.n)
+            keep |= 1u << i;
+        hits &= keep;
+      }
+      /* ordered append of the row's hits to the warp's stage (row-major == position order) */
+      if (__ballot_sync (kFull, hits != 0)) {
+        const uint32_t c = __popc (hits);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync (kFull, incl, d);
+          if (lane >= d)
+            incl += o;
+        }
+        uint32_t at = staged + incl - c;
+        const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
+        while (hits) {
+          const int i = __ffs (hits) - 1;
+          hits &= hits - 1;
+          if (at < p.stage_cap)
+            stage[at] = (uint16_t)(rel0 + i);
+          at++;
+        }
+        staged += __shfl_sync (kFull, incl, 31);
+      }
+    }
+    __syncwarp ();
+    if (staged > p.stage_cap) {
+      if (lane == 0)
+        atomicExch (p.overflow, 1u);
+      staged = p.stage_cap;
+    }
+    /* exact confirmation in the q-gram table, stable in-place compaction of the survivors */
+    uint32_t kept = 0;
+    for (uint32_t b = 0; b < staged; b += 32) {
+      const uint32_t i = b + lane;
+      uint32_t rel = 0;
+      bool ok = false;
+      if (i < staged) {
+        rel = stage[i];
+        uint64_t key;
+        uint32_t node, kw;
+        ok = qgram_key_at<W> (p, (int64_t)(tile_base + rel), &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw);
+      }
+      __syncwarp ();
+      const uint32_t mask = __ballot_sync (kFull, ok);
+      if (ok)
+        stage[kept + __popc (mask & ((1u << lane) - 1))] = (uint16_t)rel;
+      kept += __popc (mask);
+      __syncwarp ();
+    }
+    /* one reservation per tile; the tile's candidates stay contiguous and ordered */
+    uint64_t first = 0;
+    if (kept) {
+      unsigned long long seg = 0;
+      if (lane == 0)
+        seg = atomicAdd (p.cand_count, (unsigned long long)kept);
+      seg = __shfl_sync (kFull, seg, 0);
+      if (seg + kept > p.cand_cap) {
+        if (lane == 0)
+          atomicExch (p.overflow, 1u);
+        kept = 0;
+      } else {
+        first = seg;
+        for (uint32_t i = lane; i < kept; i += 32)
+          p.cand_pos[seg + i] = tile_base + stage[i];
+      }
+    }
+    if (lane == 0) {
+      p.tile_first[tile] = first;
+      p.tile_n[tile] = kept;
+    }
+    __syncwarp ();
+  }
+}
+
+/* F2 / F4: one thread per tile walks the reverse trie leftwards from each of the tile's candidates. */
+template <int W, bool kEmit>
+__global__ void __launch_bounds__ (256)
+filter_verify_kernel (const __grid_constant__ FilterParams p) {
+  const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= p.ntiles)
+    return;
+  const uint32_t n = p.tile_n[tile];
+  if (!kEmit && n == 0) {
+    p.tile_matches[tile] = 0;
+    return;
+  }
+  const uint64_t first = p.tile_first[tile];
+  uint64_t out = kEmit ? p.tile_offsets[tile] : 0;
+  uint32_t tile_total = 0;
+  for (uint32_t c = 0; c < n; c++) {
+    const int64_t pos = (int64_t)p.cand_pos[first + c];
+    uint64_t key;
+    uint32_t node, kw, found = 0;
+    const uint32_t expected = kEmit ? p.cand_matches[first + c] : 0;
+    if (qgram_key_at<W> (p, pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw)) {
+      uint32_t len = p.q;
+      for (;;) {
+        if (kw != ACM_TAB_NONE) {
+          if (kEmit) { /* found shortest first; the record order is longest first */
+            const uint64_t at = out + (expected - 1 - found);
+            if (at < p.capacity)
+              p.matches[at] = ACMB200Match{ p.base + (uint64_t)pos, kw, len };
+          }
+          found++;
+        }
+        uint32_t sym;
+        if (!symbol_at<W> (p, pos - (int64_t)len, &sym))
+          break;
+        if (!slot_lookup (p.edges, p.edge_mask, ((uint64_t)node << 32) | sym, &node, &kw))
+          break;
+        len++;
+      }
+    }
+    if (kEmit)
+      out += expected;
+    else {
+      p.cand_matches[first + c] = found;
+      tile_total += found;
+    }
+  }
+  if (!kEmit)
+    p.tile_matches[tile] = tile_total;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Position-addressable synthetic text (bench / test support)                                                          */
+/* ------------------------------------------------------------------------------------------------------------------ */
+struct GenParams {
+  uint8_t *dst;
+  uint64_t first, nb;
+  int kind;
+  uint64_t seed, plant_seed, plant_period;
+  const uint8_t *dict_symbols;
+  const uint64_t *dict_offsets;
+  uint64_t dict_nb;
+};
+
+ACM_HD uint64_t
+gen_raw64 (uint64_t seed, uint64_t k) {
+  return acm_mix64 (seed + k * 0x9E3779B97F4A7C15ull);
+}
+
+/* byte at absolute position i; identical on host and device */
+ACM_HD uint8_t
+gen_byte (const GenParams &g, uint64_t i) {
+  if (g.plant_period && g.dict_nb) {
+    /* one keyword per period; it may spill into the next period, where the next period's own plant wins */
+    const uint64_t blk = i / g.plant_period, off = i % g.plant_period;
+    for (int back = 0; back < 2; back++) {
+      if (back && blk == 0)
+        break;
+      const uint64_t b = blk - back;
+      const uint64_t r = gen_raw64 (g.plant_seed, b);
+      const uint64_t kw = (r >> 20) % g.dict_nb, at = (r & 0xFFFFFu) % g.plant_period;
+      const uint64_t lo = g.dict_offsets[kw], len = g.dict_offsets[kw + 1] - lo;
+      const uint64_t rel = off + (uint64_t)back * g.plant_period;
+      if (rel >= at && rel < at + len)
+        return g.dict_symbols[lo + (rel - at)];
+    }
+  }
+  const uint8_t b = (uint8_t)(gen_raw64 (g.seed, i >> 3) >> (8 * (i & 7)));
+  return g.kind == 1 ? (uint8_t)(0x20 + ((b * 95) >> 8)) : b;
+}
+
+__global__ void
+generate_text_kernel (const __grid_constant__ GenParams g) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v * 16 < g.nb; v += stride) {
+    const uint64_t at = v * 16;
+    if (at + 16 <= g.nb) {
+      uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        w[i >> 2] |= (uint32_t)gen_byte (g, g.first + at + i) << (8 * (i & 3));
+      *reinterpret_cast<uint4 *> (g.dst + at) = make_uint4 (w[0], w[1], w[2], w[3]);
+    } else
+      for (uint64_t i = at; i < g.nb; i++)
+        g.dst[i] = gen_byte (g, g.first + i);
+  }
+}
+
+} // namespace acm

@@ -1,0 +1,133 @@
+/* acm_b200.h -- batch (GPU) entry points of libac75.so: the data-parallel replacement of the reference's scan loop.
+ *
+ * The reference scans a text with one call per symbol (reference examples/test.c:17-23):
+ *     for each symbol:  nb = acm_match (&cursor, &text[i]);              -- aho_corasick.c:434-448 -> state_goto :167-192
+ *                       for j < nb:  acm_get_match (cursor, j, &holder); -- aho_corasick.c:451-482
+ * The functions below replace that loop for a whole text: the machine's goto/fail/output trie is compiled ("finalise")
+ * into device tables, the text is scanned on the GPU (hand-written sm_100a kernels, no CPU fallback) and every
+ * occurrence comes back as one 16-byte record.  Records are returned in the reference's own emission order:
+ * end position ascending, and for one end position longest keyword first (aho_corasick.c:459-466).
+ *
+ * Plain C ABI: pointers, sizes, integers.  Errors are returned as codes (a CUDA failure is not a contract violation,
+ * unlike the reference's ACM_ASSERT convention kept for the per-symbol API).
+ */
+#ifndef ACM_B200_H
+#define ACM_B200_H
+
+#include "aho_corasick.h"
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One occurrence.  The reference reports (cursor state, index) -> MatchHolder{letters,length,value}
+ * (aho_corasick.h:23-28,81); a record carries the same information in position-independent form. */
+typedef struct {
+  uint64_t end;     /* base + index, in symbols, of the LAST symbol of the occurrence */
+  uint32_t keyword; /* keyword id: 0-based rank among distinct keywords in first-termination order, i.e. the value of
+                       acm_nb_keywords() just before the acm_insert_end_of_keyword call that first ended it (aho_corasick.c:346-355) */
+  uint32_t length;  /* number of symbols of the keyword (MatchHolder.length, aho_corasick.c:472-474) */
+} ACMB200Match;
+
+enum {
+  ACM_B200_OK = 0,
+  ACM_B200_ERR_INVALID = 1,   /* null machine / bad argument */
+  ACM_B200_ERR_NO_DEVICE = 2, /* no CUDA device: there is no CPU fallback */
+  ACM_B200_ERR_CUDA = 3,      /* a CUDA call failed, see acm_b200_last_error */
+  ACM_B200_ERR_NOMEM = 4,
+  ACM_B200_ERR_ALPHABET = 5,  /* raw text given to a machine whose comparator needs acm_b200_remap_text */
+  ACM_B200_ERR_CAPACITY = 6   /* not an error of the scan: more records were found than `capacity`; *nb_matches holds the total */
+};
+
+enum { /* scan engines, chosen at finalise; see DESIGN.md */
+  ACM_B200_ENGINE_AUTO = 0,
+  ACM_B200_ENGINE_DFA_SMEM = 1,   /* dense delta table over byte classes, resident in shared memory */
+  ACM_B200_ENGINE_DFA_GLOBAL = 2, /* dense delta table in (L2-resident) global memory */
+  ACM_B200_ENGINE_FILTER = 3      /* exact suffix q-gram filter in shared memory + reverse-trie verification */
+};
+
+typedef struct {
+  const void *text;        /* nb_symbols symbols of acm_b200_symbol_width() bytes each; host or device memory */
+  uint64_t nb_symbols;
+  uint64_t lead;           /* the first `lead` symbols are left context only: occurrences ENDING inside them are not reported.
+                              A shard [a,b) of a larger text is scanned as text+a-lead with lead = min(a, acm_b200_max_keyword_length()-1) */
+  uint64_t base;           /* added to every reported end position (e.g. the shard's offset a-lead) */
+  int text_on_device;      /* non-zero: `text` is a device pointer on `device`, 16-byte aligned */
+  int matches_on_device;   /* non-zero: `matches` is a device pointer */
+  ACMB200Match *matches;   /* room for `capacity` records (may be 0 with capacity 0 to only count) */
+  uint64_t capacity;
+  const ACState **cursor;  /* optional, in/out: scan continues from *cursor (as acm_match would, aho_corasick.c:447) and *cursor is
+                              advanced to the state after the last symbol; 0 = start from state 0, nothing returned */
+  void *stream;            /* cudaStream_t to run on (0 = the library's own stream) */
+  int sorted;              /* 1 (default when 0 is passed via acm_b200_scan): reference order; <0: any order (set semantics) */
+} ACMB200Scan;
+
+typedef struct {
+  int engine;               /* ACM_B200_ENGINE_* actually used */
+  int symbol_width;         /* bytes per device symbol */
+  uint32_t nb_states, nb_keywords, max_keyword_length, min_keyword_length, nb_classes;
+  uint64_t table_bytes;     /* device bytes of the automaton tables */
+  uint64_t smem_bytes;      /* dynamic shared memory of the main kernel */
+  uint64_t finalise_count;  /* number of rebuild+upload cycles so far (Meyer insertions trigger one at the next scan) */
+  double finalise_ms;       /* host build + upload of the last finalise */
+  /* last scan, measured with CUDA events on the scan's stream */
+  double scan_kernel_ms;    /* first kernel start -> last kernel end (device resident input) */
+  double main_kernel_ms;    /* the text-streaming kernel(s) alone */
+  double h2d_ms, d2h_ms;
+  uint64_t last_nb_symbols, last_nb_matches, last_nb_candidates;
+  uint64_t main_kernel_launches, total_kernel_launches; /* since machine creation */
+  uint64_t fallback_count;  /* scans re-run on the DFA engine because the filter engine's candidate buffers overflowed */
+} ACMB200Stats;
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int acm_b200_device_count (void);
+
+/* Compiles the machine for `device` (-1 = current device) if it changed since the last call: cmp-ordered symbol remap,
+ * BFS state order, dense delta table / q-gram filter + reverse trie, CSR output sets; then uploads.  Idempotent; the role of the
+ * reference's lazy state_fail_state_construct guarded by `reconstruct` (aho_corasick.c:386-417).  Called implicitly by the scans. */
+int acm_b200_finalise (ACMachine *machine, int device);
+
+/* General scan. *nb_matches receives the number of occurrences found (even when larger than capacity). */
+int acm_b200_scan_ex (ACMachine *machine, const ACMB200Scan *scan, uint64_t *nb_matches);
+
+/* Convenience: host text, host records, reference order, from *cursor (may be 0). */
+int acm_b200_scan (ACMachine *machine, const ACState **cursor, const void *text, uint64_t nb_symbols, ACMB200Match *matches, uint64_t capacity,
+                   uint64_t *nb_matches);
+
+/* Bulk form of acm_insert_letter_of_keyword / acm_insert_end_of_keyword (aho_corasick.h:53,65) for packed dictionaries:
+ * keyword k = symbols[offsets[k] .. offsets[k+1]), letters of acm_b200_symbol_width() bytes, copied into machine-owned storage.
+ * Machines created with ACM_CMP_DEFAULT over 1/2/4-byte letters and no letter destructor only.  ids[k] (optional) = keyword id. */
+int acm_b200_insert_keywords (ACMachine *machine, const void *symbols, const uint64_t *offsets, uint64_t nb_keywords, uint32_t *ids);
+
+/* keyword id -> what acm_get_match would have put in the holder (letters, length, value).  The holder follows the
+ * reference's rules (acm_matcher_init before, acm_matcher_release after). */
+int acm_b200_keyword (const ACMachine *machine, uint32_t keyword, MatchHolder *holder);
+
+/* Bytes per symbol the batch scan expects: the letter size for ACM_CMP_DEFAULT machines with 1/2/4-byte letters, else 4
+ * (class ids produced by acm_b200_remap_text). */
+size_t acm_b200_symbol_width (const ACMachine *machine);
+uint32_t acm_b200_max_keyword_length (const ACMachine *machine);
+
+/* For machines with a user comparator (or a default comparator over letters that are not 1/2/4 bytes): maps `nb` letters of
+ * `letter_size` bytes to uint32 class ids with the machine's own comparator (equal under cmp <=> same id; letters that occur in no
+ * keyword get id 0).  The ids are what acm_b200_scan consumes for such machines. */
+int acm_b200_remap_text (ACMachine *machine, const void *letters, size_t letter_size, uint64_t nb, uint32_t *class_ids);
+
+/* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "tile_rows", "bloom_words", "bloom_k", "threads". */
+int acm_b200_set_option (ACMachine *machine, const char *key, const char *value);
+int acm_b200_get_stats (ACMachine *machine, ACMB200Stats *stats);
+const char *acm_b200_last_error (void);
+const char *acm_b200_version (void);
+
+/* Bench/test support (not part of the drop-in surface): position-addressable synthetic text, see DESIGN.md "Text generator".
+ * kind 0: bytes uniform 0..255; kind 1: printable ASCII 0x20 + (b*95>>8); both with keywords planted every `plant_period`
+ * symbols (0 = no plants) taken from the packed dictionary (symbols/offsets, nb_keywords).  The device variant writes device memory. */
+int acm_b200_generate_text (void *dst, int dst_on_device, uint64_t first, uint64_t nb, int kind, uint64_t seed, uint64_t plant_seed,
+                            uint64_t plant_period, const uint8_t *dict_symbols, const uint64_t *dict_offsets, uint64_t dict_nb, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,161 @@
+"""GPU parity tests (B200): every record the CUDA path returns through the C-ABI == the oracle's, bit for bit and in the
+reference's emission order, on the BASELINE.json configs at test scale, for every engine, with carried cursors, leads and shards."""
+import numpy as np
+import pytest
+
+from helpers import ac75, best_oracle_kind, config1_keywords, config2_keywords, oracle_records, pack, random_patterns
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_scan(keywords=None, flat=None, offsets=None, text=None, width=1, engine="auto", **opts):
+    m = ac75().Machine(width)
+    m.insert_many(keywords, flat=flat, offsets=offsets)
+    if engine != "auto":
+        m.set_option("engine", engine)
+    for k, v in opts.items():
+        m.set_option(k, v)
+    r = m.scan(text, capacity=max(1 << 16, 8 * len(text)))
+    st = m.stats()
+    m.close()
+    return r, st
+
+
+def test_readme_example_all_engines():
+    words = [b"he", b"she", b"his", b"hers"]
+    text = b"To ushers: he found his pencil, but she could not find hers."
+    want = oracle_records(words, text=text)
+    assert len(want) == 9
+    for engine in ("dfa_smem", "dfa_global", "filter"):
+        got, st = gpu_scan(words, text=text, engine=engine)
+        assert st["engine"] == engine
+        assert np.array_equal(got, want), engine
+
+
+@pytest.mark.parametrize("full", [False, True])
+@pytest.mark.parametrize("engine", ["auto", "dfa_global", "filter"])
+def test_config1_novel(novel, golden_config1, full, engine):
+    g = golden_config1["readme_plus_wordlist" if full else "readme_only"]
+    got, st = gpu_scan(config1_keywords(novel, full), text=novel, engine=engine)
+    assert len(got) == g["matches"]
+    assert "%016x" % pyoracle.fnv1a64_records(got) == g["fnv1a64"], st  # order-sensitive hash == the reference's emission order
+    assert [list(map(int, x)) for x in got[:48].tolist()] == g["head"]
+
+
+@pytest.mark.parametrize("engine", ["auto", "dfa_global", "filter"])
+def test_config2_words_over_ascii(novel, engine):
+    words = config2_keywords(novel)
+    flat, offsets = pack(words)
+    text = ac75().generate_text(4 << 20, kind=1, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    want = oracle_records(words, text=text, kind="port")
+    got, st = gpu_scan(words, text=text, engine=engine)
+    if engine == "auto":
+        assert st["engine"] == "dfa_smem"
+    assert len(want) > 1000 and np.array_equal(got, want), (engine, len(got), len(want))
+
+
+@pytest.mark.parametrize("engine", ["auto", "dfa_global"])
+def test_config3_random_patterns(engine):
+    flat, offsets = random_patterns(5000)
+    text = ac75().generate_text(8 << 20, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    want = oracle_records(flat=flat, offsets=offsets, text=text, kind="port")
+    got, st = gpu_scan(flat=flat, offsets=offsets, text=text, engine=engine)
+    if engine == "auto":
+        assert st["engine"] == "filter" and st["fallback_count"] == 0
+    assert len(want) >= 2000 and np.array_equal(got, want), (engine, len(got), len(want))
+
+
+@pytest.mark.parametrize("width,alphabet,lmin", [(2, 300, 2), (4, 50000, 2), (4, 3, 1), (2, 2, 1), (1, 2, 1), (1, 4, 3)])
+def test_generic_alphabets_and_dense_matches(width, alphabet, lmin):
+    rng = np.random.default_rng(width * 1000 + alphabet)
+    flat, offsets = random_patterns(300, lmin=lmin, lmax=8, seed=alphabet, alphabet=alphabet, width=width)
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[width]
+    text = rng.integers(0, alphabet, size=200_000).astype(dt)
+    # plant some keywords so that sparse alphabets have matches too
+    for k in rng.integers(0, 300, size=500):
+        kw = flat[int(offsets[k]):int(offsets[k + 1])]
+        at = int(rng.integers(0, len(text) - len(kw)))
+        text[at:at + len(kw)] = kw
+    want = oracle_records(flat=flat, offsets=offsets, text=text, width=width, kind="port")
+    engines = ["auto", "filter"] + (["dfa_global"] if width == 1 else [])
+    for engine in engines:
+        got, st = gpu_scan(flat=flat, offsets=offsets, text=text, width=width, engine=engine)
+        assert len(want) > 0 and np.array_equal(got, want), (engine, st, len(got), len(want))
+
+
+@pytest.mark.parametrize("engine", ["dfa_smem", "dfa_global", "filter"])
+def test_carried_cursor_kats(golden_kats, engine):
+    """Insertions interleaved with scanning on one carried cursor (Meyer): each insertion triggers a rebuild + re-upload."""
+    for kat in golden_kats:
+        m = ac75().Machine(kat["width"])
+        m.set_option("engine", engine)
+        for step, want in zip(kat["steps"], kat["results"]):
+            if step[0] == "insert":
+                assert m.insert_many([k.encode("latin1") for k in step[1]]).tolist() == want["ranks"], kat["name"]
+            elif step[0] == "scan":
+                got = [list(map(int, x)) for x in m.scan(step[1].encode("latin1"), carry=True).tolist()]
+                assert got == want["records"], (kat["name"], engine)
+            else:
+                m.reset_cursor()
+        m.close()
+
+
+@pytest.mark.parametrize("engine", ["dfa_global", "filter"])
+def test_incremental_rounds_random(engine):
+    """config-5 shape at test scale: rounds of insertions, each followed by a scan of the next slice with the cursor carried."""
+    rng = np.random.default_rng(5)
+    o = pyoracle.Oracle(best_oracle_kind(), 1)
+    m = ac75().Machine(1)
+    m.set_option("engine", engine)
+    stream = rng.integers(97, 101, size=60_000).astype(np.uint8)
+    for rnd in range(6):
+        kws = [stream[a:a + l].tobytes() for a, l in zip(rng.integers(0, 59_000, size=200), rng.integers(2, 9, size=200))]
+        assert np.array_equal(o.insert_many(kws), m.insert_many(kws))
+        sl = stream[rnd * 10_000:(rnd + 1) * 10_000]
+        want = o.scan(sl, base=rnd * 10_000, cap=1 << 22)
+        got = m.scan(sl, base=rnd * 10_000, carry=True, capacity=1 << 22)
+        assert np.array_equal(got, want), (engine, rnd, len(got), len(want))
+    assert m.stats()["finalise_count"] == 6
+    m.close()
+    o.close()
+
+
+@pytest.mark.parametrize("engine", ["auto", "dfa_global"])
+def test_lead_base_and_shards(engine):
+    flat, offsets = random_patterns(2000, lmin=4, lmax=32, seed=99)
+    text = ac75().generate_text(1 << 20, kind=0, plant_period=1024, dict_flat=flat, dict_offsets=offsets)
+    want = oracle_records(flat=flat, offsets=offsets, text=text, kind="port")
+    m = ac75().Machine(1)
+    m.insert_many(flat=flat, offsets=offsets)
+    m.set_option("engine", engine)
+    lmax = m.max_keyword_length
+    for world in (1, 2, 3, 8):
+        parts = []
+        for (a, b, lead) in ac75().plan_shards(len(text), world, lmax):
+            parts.append(m.scan(text[a - lead:b], lead=lead, base=a - lead))
+        got = np.concatenate(parts)
+        assert np.array_equal(got, want), (engine, world)
+    m.close()
+
+
+def test_empty_and_tiny_inputs():
+    for engine in ("dfa_smem", "dfa_global", "filter"):
+        m = ac75().Machine(1)
+        m.set_option("engine", engine)
+        assert len(m.scan(b"anything at all")) == 0  # empty dictionary (reference generic test :70)
+        m.insert_many([b"abcd"])
+        assert len(m.scan(b"")) == 0
+        assert len(m.scan(b"abc")) == 0
+        assert m.scan(b"abcd").tolist() == [(3, 0, 4)]
+        assert m.scan(b"xabcdabcd").tolist() == [(4, 0, 4), (8, 0, 4)]
+        m.close()
+
+
+def test_capacity_is_reported():
+    m = ac75().Machine(1)
+    m.insert_many([b"a"])
+    assert m.scan(b"a" * 1000, count_only=True) == 1000
+    with pytest.raises(ac75().AcmError):
+        m.scan(b"a" * 1000, capacity=10)
+    m.close()
