@@ -204,6 +204,11 @@ enter_child (struct _ac_state *n, void *letter, uint32_t at) {
   if (nprime->depth > m->max_depth)
     m->max_depth = nprime->depth;
   /* f(n') before n' is linked: delta(f(n), c), or state 0 for the children of state 0 */
+  if (m->bulk) { /* links are rebuilt in one pass by rebuild_links() */
+    add_child (n, nprime, at);
+    m->generation++;
+    return nprime;
+  }
   struct _ac_state *f = n->parent ? (struct _ac_state *)acm_host_goto (n->fail, letter) : n;
   add_child (n, nprime, at);
   ifs_add (f, nprime);
@@ -211,6 +216,33 @@ enter_child (struct _ac_state *n, void *letter, uint32_t at) {
   repoint_longer_suffixes (m, n, nprime);
   m->generation++;
   return nprime;
+}
+
+/* Whole-machine recomputation of f, IF and the output counts by one breadth-first pass (Aho-Corasick Algorithm 3,
+ * reference aho_corasick.c:386-417); used after a bulk load instead of per-node incremental maintenance. Same result. */
+static void
+rebuild_links (struct _ac_machine *m) {
+  const size_t n = m->nb_states;
+  struct _ac_state **order = malloc (n * sizeof (*order));
+  REQUIRE (order, "Out of memory.");
+  for (struct acm_state_block *b = m->blocks; b; b = b->next)
+    for (uint32_t i = 0; i < b->used; i++)
+      b->states[i].nb_ifs = 0;
+  size_t head = 0, tail = 0;
+  order[tail++] = m->root;
+  m->root->fail = 0;
+  m->root->nb_outputs = 0;
+  while (head < tail) {
+    struct _ac_state *r = order[head++];
+    for (uint32_t k = 0; k < r->nb_children; k++) {
+      struct _ac_state *s = r->children[k];
+      struct _ac_state *f = r->parent ? (struct _ac_state *)acm_host_goto (r->fail, s->letter) : r;
+      ifs_add (f, s);
+      s->nb_outputs = (s->rank != ACM_NONE ? 1u : 0u) + f->nb_outputs;
+      order[tail++] = s;
+    }
+  }
+  free (order);
 }
 
 /* ---- public: lifecycle -------------------------------------------------------------------------------------------- */
@@ -326,7 +358,8 @@ acm_insert_end_of_keyword (ACState **state, void *value, void (*dtor) (void *)) 
     }
     s->rank = (uint32_t)m->nb_sequences;
     m->keywords[m->nb_sequences++] = s;
-    count_new_output (m, s);
+    if (!m->bulk)
+      count_new_output (m, s);
     if (s->depth > m->lmax)
       m->lmax = s->depth;
     if (s->depth < m->lmin)
@@ -512,15 +545,24 @@ acm_b200_insert_keywords (ACMachine *m, const void *symbols, const uint64_t *off
   if (m->symbol_kind != ACM_SYM_RAW1 && m->symbol_kind != ACM_SYM_RAW2 && m->symbol_kind != ACM_SYM_RAW4)
     return ACM_B200_ERR_ALPHABET;
   const size_t w = m->symbol_size;
-  for (uint64_t k = 0; k < nb; k++) {
+  acm_lock (m);
+  const int bulk = nb >= 256; /* below that the incremental maintenance is cheaper than a full pass */
+  m->bulk = bulk;
+  acm_unlock (m);
+  int rc = ACM_B200_OK;
+  for (uint64_t k = 0; k < nb && rc == ACM_B200_OK; k++) {
     const size_t len = (size_t)(offsets[k + 1] - offsets[k]), bytes = (len * w + 7) & ~(size_t)7;
-    if (!len)
-      return ACM_B200_ERR_INVALID; /* the empty keyword is forbidden (reference aho_corasick.c:345) */
+    if (!len) {
+      rc = ACM_B200_ERR_INVALID; /* the empty keyword is forbidden (reference aho_corasick.c:345) */
+      break;
+    }
     if (!m->arena || m->arena->used + bytes > m->arena->cap) {
       size_t cap = bytes > (1u << 22) ? bytes : (1u << 22);
       struct acm_arena *a = malloc (sizeof (*a) + cap);
-      if (!a)
-        return ACM_B200_ERR_NOMEM;
+      if (!a) {
+        rc = ACM_B200_ERR_NOMEM;
+        break;
+      }
       a->next = m->arena;
       a->used = 0;
       a->cap = cap;
@@ -539,5 +581,11 @@ acm_b200_insert_keywords (ACMachine *m, const void *symbols, const uint64_t *off
     if (ids)
       ids[k] = id;
   }
-  return ACM_B200_OK;
+  if (bulk) {
+    acm_lock (m);
+    m->bulk = 0;
+    rebuild_links (m);
+    acm_unlock (m);
+  }
+  return rc;
 }

@@ -80,6 +80,7 @@ struct _ac_machine {
   uint32_t nb_class, cap_class;
   uint32_t *class_of_state;  /* state id -> class id of its incoming letter */
   size_t class_states_done, cap_class_states;
+  int bulk; /* set while acm_b200_insert_keywords loads many keywords: links are rebuilt by one BFS at the end */
   struct acm_arena *arena; /* letters copied by acm_b200_insert_keywords */
   /* GPU side */
   struct acm_device_image *device;

@@ -14,6 +14,8 @@
  *    while a traversal is active and reclaimed afterwards, so the snapshot never dangles;
  *  - map_find_key returns the number of elements the operator was applied to, counting an element
  *    for which the operator returned 0 (aho_corasick.c:232 relies on this);
+ *  - map_find_key with MAP_GET_ONE writes nothing to the map: the reference lets several threads scan one machine without
+ *    a lock (README.md:266,364), and the --impl reference arm of bench.py does exactly that;
  *  - no call to rand(): the reference's third test depends on the unseeded rand() sequence.
  */
 #include "map.h"
@@ -198,6 +200,10 @@ map_find_key (map *m, const void *key, map_operator op, void *op_arg, map_select
   }
   if (!n || (sel && !sel (n->data, sel_arg)))
     return 0;
+  if (op == get_one) { /* the scan path (aho_corasick.c:175) runs lock-free from many threads: strictly read-only */
+    *(void **)op_arg = n->data;
+    return 1;
+  }
   if (op) {
     int remove = 0;
     m->traversals++;
