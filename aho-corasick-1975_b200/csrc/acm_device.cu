@@ -88,7 +88,7 @@ struct acm_device_image {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_edges;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qcompact, d_edges;
   DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
@@ -105,7 +105,7 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_edges, &img->d_text, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qcompact, &img->d_edges, &img->d_text, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
@@ -176,7 +176,8 @@ finalise_locked (ACMachine *m, int device) {
   uint64_t bytes = 0;
   if (t.engine == ACM_B200_ENGINE_FILTER) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
-        || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st)))
+        || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
+        || (t.qcompact && (rc = upload (img->d_qcompact, t.qcompact, sizeof (acm_qslot) << (32 - t.qcompact_shift), st))))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot);
   } else {
@@ -192,6 +193,7 @@ finalise_locked (ACMachine *m, int device) {
   free (t.out_entries), t.out_entries = nullptr;
   free (t.bloom), t.bloom = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
+  free (t.qcompact), t.qcompact = nullptr;
   free (t.edges), t.edges = nullptr;
   m->device_generation = m->generation;
   ACMB200Stats &s = img->stats;
@@ -377,6 +379,8 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.bloom_k = t.bloom_k;
     p.qgrams = img->d_qgrams.as<acm_slot> ();
     p.qgram_mask = t.qgram_slots - 1;
+    p.qcompact = W == 4 ? nullptr : img->d_qcompact.as<acm_qslot> ();
+    p.qcompact_shift = t.qcompact_shift;
     p.edges = img->d_edges.as<acm_slot> ();
     p.edge_mask = t.edge_slots - 1;
     p.prefix = d_small->prefix;
@@ -403,7 +407,16 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.cand_count = &d_small->cand_count;
     p.overflow = &d_small->overflow;
 
-    auto f1 = filter_scan_kernel<W, kRows>;
+    void (*f1) (const FilterParams) = nullptr;
+    const int K = t.bloom_k > 2 ? 3 : 2;
+#define ACM_F1(Q_, K_) if (p.q == Q_ && K == K_) f1 = filter_scan_kernel<W, kRows, Q_, K_>
+    ACM_F1 (1, 2); ACM_F1 (1, 3); ACM_F1 (2, 2); ACM_F1 (2, 3);
+    if (W == 1) {
+      ACM_F1 (3, 2); ACM_F1 (3, 3); ACM_F1 (4, 2); ACM_F1 (4, 3);
+    }
+#undef ACM_F1
+    if (!f1)
+      return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
     CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     img->stats.smem_bytes = smem;
     /* header of Small (cand_count, grand_total, overflow) cleared; the prefix symbols follow */

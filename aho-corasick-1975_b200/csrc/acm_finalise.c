@@ -159,6 +159,7 @@ acm_free_tables (struct acm_tables *t) {
   free (t->dfa_of_state);
   free (t->bloom);
   free (t->qgrams);
+  free (t->qcompact);
   free (t->edges);
   memset (t, 0, sizeof (*t));
 }
@@ -331,6 +332,23 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
       }
       slot_find (t->qgrams, t->qgram_slots, key)->keyword = r;
     }
+  if (t->width != 4) { /* compact confirmation table, load factor <= 1/4 */
+    uint32_t bits = 10;
+    while ((1ull << bits) < 4 * nq + 16 && bits < 31)
+      bits++;
+    t->qcompact_shift = 32 - bits;
+    t->qcompact = malloc (sizeof (acm_qslot) << bits);
+    if (!t->qcompact)
+      return ACM_B200_ERR_NOMEM;
+    memset (t->qcompact, 0xFF, sizeof (acm_qslot) << bits);
+    const uint32_t mask = (1u << bits) - 1u;
+    for (uint64_t i = 0; i < nq; i++) {
+      uint32_t j = acm_qslot_hash ((uint32_t)qkeys[i], t->qcompact_shift);
+      while (t->qcompact[j].node != ACM_TAB_NONE)
+        j = (j + 1) & mask;
+      t->qcompact[j] = (acm_qslot){ (uint32_t)qkeys[i], qnodes[i] };
+    }
+  }
   /* blocked Bloom filter sized to the shared-memory budget: ~24 bits per q-gram, at most the budget */
   uint64_t want_words = m->option_bloom_words ? m->option_bloom_words : pow2_at_least ((nq * 24 + 31) / 32);
   uint64_t max_words = smem_budget / 4;
@@ -342,6 +360,8 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
   t->bloom_k = m->option_bloom_k ? (uint32_t)m->option_bloom_k : 2;
   if (t->bloom_k > 3)
     t->bloom_k = 3;
+  if (t->bloom_k < 2)
+    t->bloom_k = 2;
   t->bloom = calloc (t->bloom_words, sizeof (uint32_t));
   if (!t->bloom)
     return ACM_B200_ERR_NOMEM;

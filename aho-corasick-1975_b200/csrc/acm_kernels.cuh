@@ -214,6 +214,8 @@ struct FilterParams {
   uint32_t bloom_words, bloom_k;
   const acm_slot *qgrams;
   uint64_t qgram_mask;
+  const acm_qslot *qcompact; /* widths 1 and 2: compact copy of the q-gram keys for the confirmation step */
+  uint32_t qcompact_shift;
   const acm_slot *edges;
   uint64_t edge_mask;
   const uint32_t *prefix; /* symbols virtually preceding the text (carried cursor), prefix_len of them */
@@ -285,20 +287,48 @@ slot_lookup (const acm_slot *__restrict__ tab, uint64_t mask, uint64_t key, uint
   }
 }
 
-__device__ __forceinline__ bool
-bloom_test (const uint32_t *s_bloom, uint32_t folded, uint32_t nwords, uint32_t k) {
-  const uint32_t word = s_bloom[acm_bloom_word (folded, nwords)];
-  const uint32_t g = folded * ACM_BLOOM_C2;
-  uint32_t t = word >> (g >> 27);
-  if (k > 1)
-    t &= word >> ((g >> 22) & 31u);
-  if (k > 2)
-    t &= word >> ((g >> 17) & 31u);
-  return t & 1u;
+/* Filter test of the 16/W symbols a lane owns in one row.  Returns a mask: bit i = symbol i passed.
+ * w[0] = the 4 bytes before the lane's 16, w[1..4] = the lane's 16 bytes. */
+template <int W, int Q, int K>
+__device__ __forceinline__ uint32_t
+filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t (&w)[5]) {
+  uint32_t acc = 0; /* every test shifts its verdict in at bit 31 (one funnel shift); the first symbol ends at bit 32 - 16/W */
+  auto push = [&] (uint32_t folded) {
+    const unsigned long long p1 = (unsigned long long)folded * ACM_BLOOM_C1;
+    const uint32_t word = s_bloom[__umulhi ((uint32_t)p1, nwords)];
+    const uint32_t h1 = (uint32_t)(p1 >> 32), h2 = __umulhi (folded, ACM_BLOOM_C2);
+    uint32_t t = (word >> (h1 & 31u)) & (word >> (h2 & 31u));
+    if (K > 2)
+      t &= word >> ((h2 >> 5) & 31u);
+    acc = __funnelshift_r (acc, t, 1); /* (acc >> 1) | (t << 31): only bit 0 of t survives */
+  };
+  if (W == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      /* the 4 bytes ending at byte i: b[i-3..i], b[i] most significant */
+      const int j = (i >> 2) + 1, sh = ((i & 3) + 1) * 8;
+      const uint32_t win = sh == 32 ? w[j] : __funnelshift_r (w[j - 1], w[j], sh);
+      push (Q == 4 ? win : win >> (8 * (4 - Q)));
+    }
+    return acc >> 16;
+  } else if (W == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int j = (i >> 1) + 1;
+      const uint32_t pair = (i & 1) ? w[j] : __funnelshift_r (w[j - 1], w[j], 16); /* low half = s[i-1], high half = s[i] */
+      push (Q == 2 ? pair : (pair >> 16));
+    }
+    return acc >> 24;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      push (acm_fold_key (Q == 2 ? (((uint64_t)w[i + 1] << 32) | w[i]) : (uint64_t)w[i + 1]));
+    return acc >> 28;
+  }
 }
 
-/* F1.  One warp per tile of tile_rows x 512 bytes; lane l of row r owns the 16 bytes at r*512 + l*16. */
-template <int W, int kRows>
+/* F1.  One warp per tile of kRows x 512 bytes; lane l of row r owns the 16 bytes at r*512 + l*16. */
+template <int W, int kRows, int Q, int K>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -309,132 +339,116 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   __syncthreads ();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
   uint16_t *stage = s_stage_all + (size_t)warp * p.stage_cap;
-  constexpr int kSyms = 16 / W;          /* symbols per lane per row */
-  constexpr int kRowSyms = 32 * kSyms;   /* symbols per row */
-  const uint32_t q = p.q, nwords = p.bloom_words, bk = p.bloom_k;
+  constexpr int kSyms = 16 / W;        /* symbols per lane per row */
+  constexpr int kRowSyms = 32 * kSyms; /* symbols per row */
+  constexpr uint32_t kTileSyms = kRows * kRowSyms;
+  constexpr uint32_t q = Q;
+  const uint32_t nwords = p.bloom_words, stage_cap = p.stage_cap;
   const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
   const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
 
   for (uint64_t tile = (uint64_t)blockIdx.x * warps + warp; tile < p.ntiles; tile += (uint64_t)gridDim.x * warps) {
-    const uint64_t tile_base = tile * p.tile_syms; /* in symbols */
-    uint32_t staged = 0;                           /* warp-uniform */
+    const uint64_t tile_base = tile * kTileSyms; /* in symbols */
+    const uint8_t *tile_ptr = text8 + tile_base * W;
+    uint32_t staged = 0; /* warp-uniform */
+    /* interior tiles (every symbol reportable, every vector load inside the text) take the check-free path */
+    const bool interior = tile_base >= first_valid + 4 && tile_base + kTileSyms <= p.n;
 
     /* positions whose window reaches into the carried-cursor prefix: checked exactly, by lane 0 of the first tile */
     if (tile == 0 && p.prefix_len && q > 1) {
       if (lane == 0)
         for (uint64_t pos = p.lead; pos < min ((uint64_t)(q - 1), p.n); pos++) {
           uint64_t key;
-          if (qgram_key_at<W> (p, (int64_t)pos, &key) && staged < p.stage_cap)
-            stage[staged++] = (uint16_t)pos; /* confirmed again below like any other staged hit */
+          if (qgram_key_at<W> (p, (int64_t)pos, &key) && staged < stage_cap)
+            stage[staged++] = (uint16_t)pos; /* confirmed below like any other staged hit */
         }
       staged = __shfl_sync (kFull, staged, 0);
     }
 
     /* all rows of the tile are requested up front: kRows independent 16-byte loads per lane in flight */
     uint4 v[kRows];
-    uint32_t prev[kRows]; /* the 4 bytes before the lane's 16 */
+    if (interior) {
 #pragma unroll
-    for (int r = 0; r < kRows; r++) {
-      const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
-      if ((pos0 + kSyms) <= p.n)
-        v[r] = *reinterpret_cast<const uint4 *> (text8 + pos0 * W);
-      else {
-        uint32_t w[4] = { 0, 0, 0, 0 };
-        for (int i = 0; i < 16; i++)
-          if (pos0 * W + i < p.n * W)
-            w[i >> 2] |= (uint32_t)text8[pos0 * W + i] << (8 * (i & 3));
-        v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
-      }
-    }
+      for (int r = 0; r < kRows; r++)
+        v[r] = *reinterpret_cast<const uint4 *> (tile_ptr + r * 512 + lane * 16);
+    } else {
 #pragma unroll
-    for (int r = 0; r < kRows; r++) {
-      uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
-      if (lane == 0) {
-        if (r > 0)
-          up = 0; /* fixed below from the previous row's lane 31 */
+      for (int r = 0; r < kRows; r++) {
+        const uint64_t byte0 = (tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms) * W, nbytes = p.n * W;
+        if (byte0 + 16 <= nbytes)
+          v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
         else {
-          const uint64_t b0 = tile_base * W;
-          up = b0 >= 4 ? *reinterpret_cast<const uint32_t *> (text8 + b0 - 4) : 0;
+          uint32_t w[4] = { 0, 0, 0, 0 };
+          for (int i = 0; i < 16; i++)
+            if (byte0 + i < nbytes)
+              w[i >> 2] |= (uint32_t)text8[byte0 + i] << (8 * (i & 3));
+          v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
         }
       }
-      prev[r] = up;
     }
-#pragma unroll
-    for (int r = 1; r < kRows; r++) {
-      const uint32_t last = __shfl_sync (kFull, v[r - 1].w, 31);
-      if (lane == 0)
-        prev[r] = last;
-    }
+    const uint32_t before_tile = tile_base * W >= 4 ? *reinterpret_cast<const uint32_t *> (tile_ptr - 4) : 0;
 
+    uint32_t hits[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
-      const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
-      const uint32_t w[5] = { prev[r], v[r].x, v[r].y, v[r].z, v[r].w };
-      uint32_t hits = 0;
-      if (W == 1) {
-        const uint32_t drop = 8u * (4u - q);
+      const uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
+      const uint32_t wrap = r == 0 ? before_tile : __shfl_sync (kFull, v[r > 0 ? r - 1 : 0].w, 31);
+      const uint32_t w[5] = { lane == 0 ? wrap : up, v[r].x, v[r].y, v[r].z, v[r].w };
+      hits[r] = filter_row<W, Q, K> (s_bloom, nwords, w);
+    }
+    if (!interior) { /* drop positions outside [first_valid, n) */
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          /* the 4 bytes ending at byte i: b[i-3..i], b[i] most significant */
-          const int j = (i >> 2) + 1, sh = ((i & 3) + 1) * 8;
-          const uint32_t win = sh == 32 ? w[j] : __funnelshift_r (w[j - 1], w[j], sh);
-          if (bloom_test (s_bloom, win >> drop, nwords, bk))
-            hits |= 1u << i;
-        }
-      } else if (W == 2) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          /* symbols s[i-1], s[i]: 32 bits ending at halfword i */
-          const int j = (i >> 1) + 1;
-          const uint32_t pair = (i & 1) ? w[j] : __funnelshift_r (w[j - 1], w[j], 16); /* low half = s[i-1], high half = s[i] */
-          const uint32_t key = q == 2 ? pair : (pair >> 16);
-          if (bloom_test (s_bloom, key, nwords, bk))
-            hits |= 1u << i;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint64_t key = q == 2 ? (((uint64_t)w[i + 1] << 32) | w[i]) : (uint64_t)w[i + 1];
-          if (bloom_test (s_bloom, acm_fold_key (key), nwords, bk))
-            hits |= 1u << i;
-        }
-      }
-      /* drop positions outside [first_valid, n) */
-      if (pos0 < first_valid || pos0 + kSyms > p.n) {
+      for (int r = 0; r < kRows; r++) {
+        const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
         uint32_t keep = 0;
         for (int i = 0; i < kSyms; i++)
           if (pos0 + i >= first_valid && pos0 + i < p.n)
             keep |= 1u << i;
-        hits &= keep;
+        hits[r] &= keep;
       }
-      /* ordered append of the row's hits to the warp's stage (row-major == position order) */
-      if (__ballot_sync (kFull, hits != 0)) {
-        const uint32_t c = __popc (hits);
-        uint32_t incl = c;
+    }
+    /* Ordered append of the tile's hits to the warp's stage.  Position order is (row, lane, symbol): one warp scan over the
+     * per-row counts of every lane, two rows packed per 32-bit word (a row holds at most 512 hits). */
+    {
+      uint32_t incl[(kRows + 1) / 2];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync (kFull, incl, d);
+      for (int h = 0; h < (kRows + 1) / 2; h++)
+        incl[h] = __popc (hits[2 * h]) | ((2 * h + 1 < kRows ? __popc (hits[2 * h + 1]) : 0) << 16);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+        for (int h = 0; h < (kRows + 1) / 2; h++) {
+          const uint32_t o = __shfl_up_sync (kFull, incl[h], d);
           if (lane >= d)
-            incl += o;
+            incl[h] += o;
         }
-        uint32_t at = staged + incl - c;
+      }
+      uint32_t row_start = staged;
+#pragma unroll
+      for (int r = 0; r < kRows; r++) {
+        const uint32_t mine = (incl[r >> 1] >> (16 * (r & 1))) & 0xFFFFu; /* inclusive count up to this lane */
+        const uint32_t total = __shfl_sync (kFull, mine, 31);
+        uint32_t at = row_start + mine - __popc (hits[r]);
+        uint32_t h = hits[r];
         const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
-        while (hits) {
-          const int i = __ffs (hits) - 1;
-          hits &= hits - 1;
-          if (at < p.stage_cap)
+        while (h) {
+          const int i = __ffs (h) - 1;
+          h &= h - 1;
+          if (at < stage_cap)
             stage[at] = (uint16_t)(rel0 + i);
           at++;
         }
-        staged += __shfl_sync (kFull, incl, 31);
+        row_start += total;
       }
+      staged = row_start;
     }
     __syncwarp ();
-    if (staged > p.stage_cap) {
+    if (staged > stage_cap) {
       if (lane == 0)
         atomicExch (p.overflow, 1u);
-      staged = p.stage_cap;
+      staged = stage_cap;
     }
     /* exact confirmation in the q-gram table, stable in-place compaction of the survivors */
     uint32_t kept = 0;
@@ -444,14 +458,36 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       bool ok = false;
       if (i < staged) {
         rel = stage[i];
-        uint64_t key;
-        uint32_t node, kw;
-        ok = qgram_key_at<W> (p, (int64_t)(tile_base + rel), &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw);
+        const uint64_t pos = tile_base + rel;
+        if (W != 4 && interior) { /* every byte touched lies inside this tile or the 4 bytes before it */
+          /* the Q symbols ending at pos, rebuilt from two aligned 32-bit loads */
+          const uint64_t last_byte = pos * W + (W - 1);      /* last byte of the window */
+          const uint64_t first4 = last_byte - 3;             /* the 4 bytes ending there */
+          const uint32_t *t32 = reinterpret_cast<const uint32_t *> (text8 + (first4 & ~(uint64_t)3));
+          const uint32_t win = __funnelshift_r (t32[0], (first4 & 3) ? t32[1] : 0u, 8 * (uint32_t)(first4 & 3));
+          const uint32_t key = W == 1 ? (Q == 4 ? win : win >> (8 * (4 - Q))) : (Q == 2 ? win : win >> 16);
+          const uint32_t mask = (1u << (32 - p.qcompact_shift)) - 1u;
+          uint32_t j = acm_qslot_hash (key, p.qcompact_shift);
+          for (;;) {
+            const uint2 slot = __ldg (reinterpret_cast<const uint2 *> (p.qcompact + j));
+            if (slot.y == ACM_TAB_NONE)
+              break;
+            if (slot.x == key) {
+              ok = true;
+              break;
+            }
+            j = (j + 1) & mask;
+          }
+        } else {
+          uint64_t key;
+          uint32_t node, kw;
+          ok = qgram_key_at<W> (p, (int64_t)pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw);
+        }
       }
       __syncwarp ();
       const uint32_t mask = __ballot_sync (kFull, ok);
       if (ok)
-        stage[kept + __popc (mask & ((1u << lane) - 1))] = (uint16_t)rel;
+        stage[kept + __popc (mask & lanes_below)] = (uint16_t)rel;
       kept += __popc (mask);
       __syncwarp ();
     }

@@ -31,25 +31,30 @@ acm_fold_key (uint64_t key) {
 
 #define ACM_BLOOM_C1 0x9E3779B1u
 #define ACM_BLOOM_C2 0x85EBCA77u
-/* word index of a folded key in a filter of nwords 32-bit words (nwords need not be a power of two) */
+/* Blocked Bloom filter in shared memory: one 32-bit word per key, k (2 or 3) bits inside it.
+ *   p1 = folded * C1 (64-bit product): word index = mulhi (lo32 (p1), nwords)   (nwords need not be a power of two)
+ *                                      bit a      = hi32 (p1) & 31              (bits 32..36 of the product: depend on every input bit)
+ *   h2 = mulhi (folded, C2):           bit b      = h2 & 31,   bit c = (h2 >> 5) & 31
+ * The bit positions sit in the low 5 bits of a register on purpose: the GPU's funnel shift takes its amount modulo 32, so the
+ * kernel needs no extraction instruction, and the multiplies run on the FMA pipe next to the ALU pipe that does the shifts. */
 ACM_HD uint32_t
-acm_bloom_word (uint32_t folded, uint32_t nwords) {
-  uint32_t h = folded * ACM_BLOOM_C1;
+acm_mulhi32 (uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
-  return __umulhi (h, nwords);
+  return __umulhi (a, b);
 #else
-  return (uint32_t)(((uint64_t)h * nwords) >> 32);
+  return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-/* k (1..3) bit positions inside the word, from an independent multiplicative hash */
+ACM_HD uint32_t
+acm_bloom_word (uint32_t folded, uint32_t nwords) {
+  return acm_mulhi32 (folded * ACM_BLOOM_C1, nwords);
+}
 ACM_HD uint32_t
 acm_bloom_mask (uint32_t folded, uint32_t k) {
-  uint32_t g = folded * ACM_BLOOM_C2;
-  uint32_t m = 1u << (g >> 27);
-  if (k > 1)
-    m |= 1u << ((g >> 22) & 31u);
+  const uint32_t h1 = acm_mulhi32 (folded, ACM_BLOOM_C1), h2 = acm_mulhi32 (folded, ACM_BLOOM_C2);
+  uint32_t m = (1u << (h1 & 31u)) | (1u << (h2 & 31u));
   if (k > 2)
-    m |= 1u << ((g >> 17) & 31u);
+    m |= 1u << ((h2 >> 5) & 31u);
   return m;
 }
 
@@ -63,6 +68,17 @@ typedef struct {
   uint32_t keyword;
 } acm_slot;
 #define ACM_TAB_NONE 0xFFFFFFFFu
+
+/* Compact q-gram table for keys that fit 32 bits (byte and 16-bit alphabets): 8-byte slots {key, node}, one multiply to hash.
+ * node == ACM_TAB_NONE marks an empty slot.  The keyword ending exactly at the q-gram (if any) is looked up in `qgrams` later. */
+typedef struct {
+  uint32_t key;
+  uint32_t node;
+} acm_qslot;
+ACM_HD uint32_t
+acm_qslot_hash (uint32_t key, uint32_t shift) {
+  return (key * 0x9E3779B1u) >> shift; /* top bits of a multiplicative hash; slots = 1 << (32 - shift) */
+}
 
 typedef struct {
   uint32_t keyword;
@@ -91,6 +107,8 @@ struct acm_tables {
   uint32_t bloom_words, bloom_k;
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
+  acm_qslot *qcompact;        /* same keys, compact form, widths 1 and 2 only */
+  uint32_t qcompact_shift;    /* slots = 1 << (32 - shift) */
   acm_slot *edges;
   uint64_t edge_slots;        /* power of two */
   uint32_t nb_rev_nodes;
