@@ -88,8 +88,8 @@ struct acm_device_image {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qcompact, d_edges;
-  DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_tile_first, d_tile_n, d_small;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qset, d_edges;
+  DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
@@ -105,8 +105,8 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qcompact, &img->d_edges, &img->d_text, &img->d_matches,
-                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_tile_first, &img->d_tile_n, &img->d_small })
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_text, &img->d_matches,
+                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
     if (e)
@@ -167,7 +167,7 @@ finalise_locked (ACMachine *m, int device) {
   const auto t0 = std::chrono::steady_clock::now ();
   acm_free_tables (&img->tab);
   /* shared-memory budget for the resident table: everything a block may opt in to, minus class map / staging / slack */
-  const uint64_t budget = img->smem_optin - 32 * 256 * 2 - 2048;
+  const uint64_t budget = img->smem_optin - 32 * (192 * 2 + 16) - 2048;
   int rc = acm_build_tables (m, &img->tab, budget);
   if (rc)
     return fail (rc, "building the automaton tables failed%s", "");
@@ -177,7 +177,7 @@ finalise_locked (ACMachine *m, int device) {
   if (t.engine == ACM_B200_ENGINE_FILTER) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
         || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
-        || (t.qcompact && (rc = upload (img->d_qcompact, t.qcompact, sizeof (acm_qslot) << (32 - t.qcompact_shift), st))))
+        || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st))))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot);
   } else {
@@ -193,7 +193,7 @@ finalise_locked (ACMachine *m, int device) {
   free (t.out_entries), t.out_entries = nullptr;
   free (t.bloom), t.bloom = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
-  free (t.qcompact), t.qcompact = nullptr;
+  free (t.qset), t.qset = nullptr;
   free (t.edges), t.edges = nullptr;
   m->device_generation = m->generation;
   ACMB200Stats &s = img->stats;
@@ -379,15 +379,16 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.bloom_k = t.bloom_k;
     p.qgrams = img->d_qgrams.as<acm_slot> ();
     p.qgram_mask = t.qgram_slots - 1;
-    p.qcompact = W == 4 ? nullptr : img->d_qcompact.as<acm_qslot> ();
-    p.qcompact_shift = t.qcompact_shift;
+    p.qset = W == 4 ? nullptr : img->d_qset.as<uint4> ();
+    p.qset_shift = t.qset_shift;
+    p.qset_has_empty_key = t.qset_has_empty_key;
     p.edges = img->d_edges.as<acm_slot> ();
     p.edge_mask = t.edge_slots - 1;
     p.prefix = d_small->prefix;
     p.prefix_len = job.prefix_len;
-    p.stage_cap = dense ? p.tile_syms : 256;
+    p.stage_cap = dense ? p.tile_syms : 192;
     p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / 32, 1u << 16);
-    size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2;
+    size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
     int warps = 32;
     while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
       warps /= 2;
@@ -395,11 +396,13 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     if (smem > img->smem_optin)
       return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
     int rc;
-    if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
+    if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = img->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
         || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
       return rc;
     p.cand_pos = img->d_cand_pos.as<uint64_t> ();
     p.cand_matches = img->d_cand_matches.as<uint32_t> ();
+    p.cand_prefix = img->d_cand_prefix.as<uint32_t> ();
+    p.cand_inline = img->d_cand_inline.as<uint4> ();
     p.tile_first = img->d_tile_first.as<uint64_t> ();
     p.tile_n = img->d_tile_n.as<uint32_t> ();
     p.tile_matches = img->d_counts.as<uint32_t> ();
@@ -408,8 +411,9 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.overflow = &d_small->overflow;
 
     void (*f1) (const FilterParams) = nullptr;
+    const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
     const int K = t.bloom_k > 2 ? 3 : 2;
-#define ACM_F1(Q_, K_) if (p.q == Q_ && K == K_) f1 = filter_scan_kernel<W, kRows, Q_, K_>
+#define ACM_F1(Q_, K_) if (p.q == Q_ && K == K_) f1 = ordered ? filter_scan_kernel<W, kRows, Q_, K_, true> : filter_scan_kernel<W, kRows, Q_, K_, false>
     ACM_F1 (1, 2); ACM_F1 (1, 3); ACM_F1 (2, 2); ACM_F1 (2, 3);
     if (W == 1) {
       ACM_F1 (3, 2); ACM_F1 (3, 3); ACM_F1 (4, 2); ACM_F1 (4, 3);
@@ -429,23 +433,33 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     f1<<<grid, warps * 32, smem, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
     CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
-    const unsigned vgrid = (unsigned)((p.ntiles + 255) / 256);
-    filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p);
-    CUDA_TRY (cudaGetLastError ());
-    if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
-      return rc;
+    /* the number of candidates decides the grid of the verification kernels (and tells whether a buffer overflowed) */
     CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
     CUDA_TRY (cudaStreamSynchronize (job.st));
     img->stats.main_kernel_launches += 1;
-    img->stats.total_kernel_launches += 2;
+    img->stats.total_kernel_launches += 1;
     if (img->h_small->overflow) {
       img->stats.fallback_count++;
       if (dense)
         return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
       continue;
     }
+    const uint64_t nb_cand = img->h_small->cand_count;
+    const unsigned vgrid = (unsigned)((nb_cand + 255) / 256), tgrid = (unsigned)((p.ntiles + 255) / 256);
+    if (nb_cand) {
+      filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p, nb_cand);
+      CUDA_TRY (cudaGetLastError ());
+      img->stats.total_kernel_launches += 1;
+    }
+    filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
+    CUDA_TRY (cudaGetLastError ());
+    img->stats.total_kernel_launches += 1;
+    if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+      return rc;
+    CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
+    CUDA_TRY (cudaStreamSynchronize (job.st));
     *total = img->h_small->grand_total;
-    img->stats.last_nb_candidates = img->h_small->cand_count;
+    img->stats.last_nb_candidates = nb_cand;
     const uint64_t want = std::min<uint64_t> (*total, job.capacity);
     CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
     if (want) {
@@ -457,7 +471,7 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
         p.matches = img->d_matches.as<ACMB200Match> ();
       }
       p.capacity = want;
-      filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p);
+      filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p, nb_cand);
       CUDA_TRY (cudaGetLastError ());
       img->stats.total_kernel_launches += 1;
     }

@@ -159,7 +159,7 @@ acm_free_tables (struct acm_tables *t) {
   free (t->dfa_of_state);
   free (t->bloom);
   free (t->qgrams);
-  free (t->qcompact);
+  free (t->qset);
   free (t->edges);
   memset (t, 0, sizeof (*t));
 }
@@ -332,21 +332,28 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
       }
       slot_find (t->qgrams, t->qgram_slots, key)->keyword = r;
     }
-  if (t->width != 4) { /* compact confirmation table, load factor <= 1/4 */
-    uint32_t bits = 10;
-    while ((1ull << bits) < 4 * nq + 16 && bits < 31)
+  if (t->width != 4) { /* compact confirmation set, load factor <= 1/4 */
+    uint32_t bits = 8;
+    while ((4ull << bits) < 4 * nq + 16 && bits < 29)
       bits++;
-    t->qcompact_shift = 32 - bits;
-    t->qcompact = malloc (sizeof (acm_qslot) << bits);
-    if (!t->qcompact)
+    t->qset_shift = 32 - bits;
+    t->qset = malloc ((size_t)16 << bits);
+    if (!t->qset)
       return ACM_B200_ERR_NOMEM;
-    memset (t->qcompact, 0xFF, sizeof (acm_qslot) << bits);
+    memset (t->qset, 0xFF, (size_t)16 << bits);
     const uint32_t mask = (1u << bits) - 1u;
     for (uint64_t i = 0; i < nq; i++) {
-      uint32_t j = acm_qslot_hash ((uint32_t)qkeys[i], t->qcompact_shift);
-      while (t->qcompact[j].node != ACM_TAB_NONE)
-        j = (j + 1) & mask;
-      t->qcompact[j] = (acm_qslot){ (uint32_t)qkeys[i], qnodes[i] };
+      const uint32_t key = (uint32_t)qkeys[i];
+      if (key == ACM_QSET_EMPTY) {
+        t->qset_has_empty_key = 1;
+        continue;
+      }
+      for (uint32_t b = acm_qset_bucket (key, t->qset_shift), placed = 0; !placed; b = (b + 1) & mask)
+        for (int c = 0; c < 4 && !placed; c++)
+          if (t->qset[4 * (size_t)b + c] == ACM_QSET_EMPTY) {
+            t->qset[4 * (size_t)b + c] = key;
+            placed = 1;
+          }
     }
   }
   /* blocked Bloom filter sized to the shared-memory budget: ~24 bits per q-gram, at most the budget */

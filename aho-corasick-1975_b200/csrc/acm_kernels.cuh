@@ -214,8 +214,8 @@ struct FilterParams {
   uint32_t bloom_words, bloom_k;
   const acm_slot *qgrams;
   uint64_t qgram_mask;
-  const acm_qslot *qcompact; /* widths 1 and 2: compact copy of the q-gram keys for the confirmation step */
-  uint32_t qcompact_shift;
+  const uint4 *qset; /* widths 1 and 2: the q-gram keys as a compact set, 4 keys per 16-byte bucket (acm_tables.h) */
+  uint32_t qset_shift, qset_has_empty_key;
   const acm_slot *edges;
   uint64_t edge_mask;
   const uint32_t *prefix; /* symbols virtually preceding the text (carried cursor), prefix_len of them */
@@ -230,6 +230,8 @@ struct FilterParams {
   uint32_t *overflow;
   /* F2 out / F4 in */
   uint32_t *cand_matches;
+  uint32_t *cand_prefix; /* matches of the candidates before this one in its tile (written by F3) */
+  uint4 *cand_inline;    /* the first two matches of the candidate {keyword, length, keyword, length}, shortest first (written by F2) */
   uint32_t *tile_matches;
   const uint64_t *tile_offsets;
   ACMB200Match *matches;
@@ -327,20 +329,40 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t (&w)[5]) {
   }
 }
 
-/* F1.  One warp per tile of kRows x 512 bytes; lane l of row r owns the 16 bytes at r*512 + l*16. */
-template <int W, int kRows, int Q, int K>
+/* Membership of a 32-bit q-gram key in the compact set: normally one 16-byte load. */
+__device__ __forceinline__ bool
+qset_contains (const FilterParams &p, uint32_t key) {
+  if (key == ACM_QSET_EMPTY)
+    return p.qset_has_empty_key != 0;
+  const uint32_t mask = (1u << (32 - p.qset_shift)) - 1u;
+  for (uint32_t b = acm_qset_bucket (key, p.qset_shift);; b = (b + 1) & mask) {
+    const uint4 c = __ldg (p.qset + b);
+    if (c.x == key || c.y == key || c.z == key || c.w == key)
+      return true;
+    if (c.x == ACM_QSET_EMPTY || c.y == ACM_QSET_EMPTY || c.z == ACM_QSET_EMPTY || c.w == ACM_QSET_EMPTY)
+      return false;
+  }
+}
+
+/* F1.  One warp per tile of kRows x 512 bytes; lane l of row r owns the 16 bytes at r*512 + l*16.
+ * kOrdered: raw hits are staged in position order with a warp scan (used by the dense fallback, where a tile may hold thousands
+ * of candidates); otherwise they are staged through a shared-memory counter in any order and the few survivors of the exact
+ * confirmation are sorted afterwards -- fewer instructions when hits are rare. */
+template <int W, int kRows, int Q, int K, bool kOrdered>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
   uint32_t *s_bloom = reinterpret_cast<uint32_t *> (smem);
-  uint16_t *s_stage_all = reinterpret_cast<uint16_t *> (smem + (size_t)p.bloom_words * 4);
+  unsigned char *s_stage_all = smem + (size_t)p.bloom_words * 4;
   for (uint32_t i = threadIdx.x; i < p.bloom_words; i += blockDim.x)
     s_bloom[i] = p.bloom[i];
   __syncthreads ();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
-  uint16_t *stage = s_stage_all + (size_t)warp * p.stage_cap;
+  /* per warp: a 16-byte header (hit counter) then stage_cap 16-bit tile-relative positions */
+  uint32_t *stage_count = reinterpret_cast<uint32_t *> (s_stage_all + (size_t)warp * (p.stage_cap * 2 + 16));
+  uint16_t *stage = reinterpret_cast<uint16_t *> (stage_count + 4);
   constexpr int kSyms = 16 / W;        /* symbols per lane per row */
   constexpr int kRowSyms = 32 * kSyms; /* symbols per row */
   constexpr uint32_t kTileSyms = kRows * kRowSyms;
@@ -353,6 +375,11 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
     const uint64_t tile_base = tile * kTileSyms; /* in symbols */
     const uint8_t *tile_ptr = text8 + tile_base * W;
     uint32_t staged = 0; /* warp-uniform */
+    { /* pull this warp's next tile from DRAM into L2 while the current one is being processed */
+      const uint64_t next = tile + (uint64_t)gridDim.x * warps;
+      if (next < p.ntiles && lane < kRows * 4)
+        asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + next * (kTileSyms * W) + lane * 128));
+    }
     /* interior tiles (every symbol reportable, every vector load inside the text) take the check-free path */
     const bool interior = tile_base >= first_valid + 4 && tile_base + kTileSyms <= p.n;
 
@@ -365,6 +392,11 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
             stage[staged++] = (uint16_t)pos; /* confirmed below like any other staged hit */
         }
       staged = __shfl_sync (kFull, staged, 0);
+    }
+    if (!kOrdered) {
+      if (lane == 0)
+        *stage_count = staged;
+      __syncwarp ();
     }
 
     /* all rows of the tile are requested up front: kRows independent 16-byte loads per lane in flight */
@@ -409,9 +441,10 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         hits[r] &= keep;
       }
     }
-    /* Ordered append of the tile's hits to the warp's stage.  Position order is (row, lane, symbol): one warp scan over the
-     * per-row counts of every lane, two rows packed per 32-bit word (a row holds at most 512 hits). */
-    {
+
+    if (kOrdered) {
+      /* Ordered append.  Position order is (row, lane, symbol): one warp scan over the per-row counts of every lane, two rows
+       * packed per 32-bit word (a row holds at most 512 hits). */
       uint32_t incl[(kRows + 1) / 2];
 #pragma unroll
       for (int h = 0; h < (kRows + 1) / 2; h++)
@@ -443,53 +476,106 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         row_start += total;
       }
       staged = row_start;
+      __syncwarp ();
+    } else {
+      /* Unordered append through the warp's shared counter: only lanes that have hits do any work. */
+      uint32_t mine = 0;
+#pragma unroll
+      for (int r = 0; r < kRows; r++)
+        mine += __popc (hits[r]);
+      if (mine) {
+        uint32_t at = atomicAdd (stage_count, mine);
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+          uint32_t h = hits[r];
+          const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
+          while (h) {
+            const int i = __ffs (h) - 1;
+            h &= h - 1;
+            if (at < stage_cap)
+              stage[at] = (uint16_t)(rel0 + i);
+            at++;
+          }
+        }
+      }
+      __syncwarp ();
+      staged = *stage_count;
     }
-    __syncwarp ();
     if (staged > stage_cap) {
       if (lane == 0)
         atomicExch (p.overflow, 1u);
       staged = stage_cap;
     }
-    /* exact confirmation in the q-gram table, stable in-place compaction of the survivors */
+
+    /* Exact confirmation of the staged hits in the q-gram table; survivors are compacted in place (stable). Two batches are
+     * in flight at a time so that the dependent L2 round trips (text, then table) overlap. */
     uint32_t kept = 0;
-    for (uint32_t b = 0; b < staged; b += 32) {
-      const uint32_t i = b + lane;
-      uint32_t rel = 0;
-      bool ok = false;
-      if (i < staged) {
-        rel = stage[i];
-        const uint64_t pos = tile_base + rel;
-        if (W != 4 && interior) { /* every byte touched lies inside this tile or the 4 bytes before it */
-          /* the Q symbols ending at pos, rebuilt from two aligned 32-bit loads */
-          const uint64_t last_byte = pos * W + (W - 1);      /* last byte of the window */
-          const uint64_t first4 = last_byte - 3;             /* the 4 bytes ending there */
-          const uint32_t *t32 = reinterpret_cast<const uint32_t *> (text8 + (first4 & ~(uint64_t)3));
-          const uint32_t win = __funnelshift_r (t32[0], (first4 & 3) ? t32[1] : 0u, 8 * (uint32_t)(first4 & 3));
-          const uint32_t key = W == 1 ? (Q == 4 ? win : win >> (8 * (4 - Q))) : (Q == 2 ? win : win >> 16);
-          const uint32_t mask = (1u << (32 - p.qcompact_shift)) - 1u;
-          uint32_t j = acm_qslot_hash (key, p.qcompact_shift);
-          for (;;) {
-            const uint2 slot = __ldg (reinterpret_cast<const uint2 *> (p.qcompact + j));
-            if (slot.y == ACM_TAB_NONE)
-              break;
-            if (slot.x == key) {
-              ok = true;
-              break;
-            }
-            j = (j + 1) & mask;
+    for (uint32_t b = 0; b < staged; b += 64) {
+      uint32_t rel[2] = { 0, 0 }, key[2] = { 0, 0 };
+      bool live[2], ok[2] = { false, false };
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t i = b + 32 * u + lane;
+        live[u] = i < staged;
+        if (live[u]) {
+          rel[u] = stage[i];
+          if (W != 4 && interior) { /* the Q symbols ending at the position, rebuilt from two aligned 32-bit loads inside the tile */
+            const uint64_t first4 = (tile_base + rel[u]) * W + (W - 1) - 3;
+            const uint32_t *t32 = reinterpret_cast<const uint32_t *> (text8 + (first4 & ~(uint64_t)3));
+            const uint32_t win = __funnelshift_r (t32[0], t32[1], 8 * (uint32_t)(first4 & 3));
+            key[u] = W == 1 ? (Q == 4 ? win : win >> (8 * (4 - Q))) : (Q == 2 ? win : win >> 16);
           }
-        } else {
-          uint64_t key;
-          uint32_t node, kw;
-          ok = qgram_key_at<W> (p, (int64_t)pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw);
         }
       }
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+        if (live[u]) {
+          if (W != 4 && interior)
+            ok[u] = qset_contains (p, key[u]);
+          else {
+            uint64_t k64;
+            uint32_t node, kw;
+            ok[u] = qgram_key_at<W> (p, (int64_t)(tile_base + rel[u]), &k64) && slot_lookup (p.qgrams, p.qgram_mask, k64, &node, &kw);
+          }
+        }
       __syncwarp ();
-      const uint32_t mask = __ballot_sync (kFull, ok);
-      if (ok)
-        stage[kept + __popc (mask & lanes_below)] = (uint16_t)rel;
-      kept += __popc (mask);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t mask = __ballot_sync (kFull, ok[u]);
+        if (ok[u])
+          stage[kept + __popc (mask & lanes_below)] = (uint16_t)rel[u];
+        kept += __popc (mask);
+      }
       __syncwarp ();
+    }
+    if (!kOrdered && kept > stage_cap / 2) { /* the sort below needs half of the stage as scratch: leave it to the dense mode */
+      if (lane == 0)
+        atomicExch (p.overflow, 1u);
+      kept = 0;
+    }
+    if (!kOrdered && kept > 1) {
+      /* sort the survivors by position (they are few): rank = number of smaller positions */
+      for (uint32_t b = 0; b < kept; b += 32) {
+        const uint32_t i = b + lane;
+        uint32_t mine = i < kept ? stage[i] : 0xFFFFFFFFu, rank = 0;
+        for (uint32_t j = 0; j < kept; j++)
+          rank += stage[j] < mine;
+        __syncwarp ();
+        /* positions are distinct, so ranks are a permutation; write through a second pass to avoid overwriting unread entries */
+        if (b + 32 >= kept && b == 0) {
+          if (i < kept)
+            stage[rank] = (uint16_t)mine;
+        } else { /* more than 32 survivors: use the upper half of the stage as scratch */
+          if (i < kept)
+            stage[stage_cap / 2 + rank] = (uint16_t)mine;
+        }
+        __syncwarp ();
+      }
+      if (kept > 32) {
+        for (uint32_t i = lane; i < kept; i += 32)
+          stage[i] = stage[stage_cap / 2 + i];
+        __syncwarp ();
+      }
     }
     /* one reservation per tile; the tile's candidates stay contiguous and ordered */
     uint64_t first = 0;
@@ -516,54 +602,88 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   }
 }
 
-/* F2 / F4: one thread per tile walks the reverse trie leftwards from each of the tile's candidates. */
+/* F2 / F4: one thread per candidate walks the reverse trie leftwards from the candidate's position.
+ * F2 (kEmit = false) counts the keywords ending there; F3 sums the counts of each tile (its candidates are contiguous and in
+ * position order); after the device scan of the tile totals, F4 (kEmit = true) walks again and writes the records of the
+ * candidate at tile offset + the counts of the candidates before it in the tile, longest keyword first. */
 template <int W, bool kEmit>
 __global__ void __launch_bounds__ (256)
-filter_verify_kernel (const __grid_constant__ FilterParams p) {
+filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candidates) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb_candidates)
+    return;
+  const int64_t pos = (int64_t)p.cand_pos[c];
+  uint32_t expected = 0;
+  uint64_t out = 0;
+  if (kEmit) {
+    expected = p.cand_matches[c];
+    if (!expected)
+      return;
+    const uint64_t tile = (uint64_t)pos / p.tile_syms, first = 0;
+    (void)first;
+    out = p.tile_offsets[tile] + p.cand_prefix[c];
+    if (expected <= 2) { /* usual case: the counting pass kept them, no second walk */
+      const uint4 m = p.cand_inline[c];
+      if (expected == 2) {
+        if (out < p.capacity)
+          p.matches[out] = ACMB200Match{ p.base + (uint64_t)pos, m.z, m.w };
+        out++;
+      }
+      if (out < p.capacity)
+        p.matches[out] = ACMB200Match{ p.base + (uint64_t)pos, m.x, m.y };
+      return;
+    }
+  }
+  uint4 first_two = make_uint4 (0, 0, 0, 0);
+  uint64_t key;
+  uint32_t node, kw, found = 0;
+  if (qgram_key_at<W> (p, pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw)) {
+    uint32_t len = p.q;
+    for (;;) {
+      if (kw != ACM_TAB_NONE) {
+        if (kEmit) { /* found shortest first; the record order is longest first */
+          const uint64_t at = out + (expected - 1 - found);
+          if (at < p.capacity)
+            p.matches[at] = ACMB200Match{ p.base + (uint64_t)pos, kw, len };
+        } else if (found == 0) {
+          first_two.x = kw;
+          first_two.y = len;
+        } else if (found == 1) {
+          first_two.z = kw;
+          first_two.w = len;
+        }
+        found++;
+      }
+      uint32_t sym;
+      if (!symbol_at<W> (p, pos - (int64_t)len, &sym))
+        break;
+      if (!slot_lookup (p.edges, p.edge_mask, ((uint64_t)node << 32) | sym, &node, &kw))
+        break;
+      len++;
+    }
+  }
+  if (!kEmit) {
+    p.cand_matches[c] = found;
+    p.cand_inline[c] = first_two;
+  }
+}
+
+/* F3: matches per tile = sum over the tile's candidates; also the running prefix of every candidate inside its tile. */
+__global__ void __launch_bounds__ (256)
+filter_tile_totals_kernel (const __grid_constant__ FilterParams p) {
   const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= p.ntiles)
     return;
   const uint32_t n = p.tile_n[tile];
-  if (!kEmit && n == 0) {
-    p.tile_matches[tile] = 0;
-    return;
-  }
-  const uint64_t first = p.tile_first[tile];
-  uint64_t out = kEmit ? p.tile_offsets[tile] : 0;
-  uint32_t tile_total = 0;
-  for (uint32_t c = 0; c < n; c++) {
-    const int64_t pos = (int64_t)p.cand_pos[first + c];
-    uint64_t key;
-    uint32_t node, kw, found = 0;
-    const uint32_t expected = kEmit ? p.cand_matches[first + c] : 0;
-    if (qgram_key_at<W> (p, pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw)) {
-      uint32_t len = p.q;
-      for (;;) {
-        if (kw != ACM_TAB_NONE) {
-          if (kEmit) { /* found shortest first; the record order is longest first */
-            const uint64_t at = out + (expected - 1 - found);
-            if (at < p.capacity)
-              p.matches[at] = ACMB200Match{ p.base + (uint64_t)pos, kw, len };
-          }
-          found++;
-        }
-        uint32_t sym;
-        if (!symbol_at<W> (p, pos - (int64_t)len, &sym))
-          break;
-        if (!slot_lookup (p.edges, p.edge_mask, ((uint64_t)node << 32) | sym, &node, &kw))
-          break;
-        len++;
-      }
-    }
-    if (kEmit)
-      out += expected;
-    else {
-      p.cand_matches[first + c] = found;
-      tile_total += found;
+  uint32_t total = 0;
+  if (n) {
+    const uint64_t first = p.tile_first[tile];
+    for (uint32_t j = 0; j < n; j++) {
+      p.cand_prefix[first + j] = total;
+      total += p.cand_matches[first + j];
     }
   }
-  if (!kEmit)
-    p.tile_matches[tile] = tile_total;
+  p.tile_matches[tile] = total;
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */

@@ -69,15 +69,14 @@ typedef struct {
 } acm_slot;
 #define ACM_TAB_NONE 0xFFFFFFFFu
 
-/* Compact q-gram table for keys that fit 32 bits (byte and 16-bit alphabets): 8-byte slots {key, node}, one multiply to hash.
- * node == ACM_TAB_NONE marks an empty slot.  The keyword ending exactly at the q-gram (if any) is looked up in `qgrams` later. */
-typedef struct {
-  uint32_t key;
-  uint32_t node;
-} acm_qslot;
+/* Compact q-gram key set for keys that fit 32 bits (byte and 16-bit alphabets), used by the confirmation step of the filter kernel:
+ * buckets of 4 keys (16 bytes = one vector load); a key lives in its home bucket or, if that is full, in the next ones.
+ * Empty cells hold ACM_QSET_EMPTY; a dictionary whose q-gram equals that value sets qset_has_empty_key instead of storing it.
+ * A lookup reads the home bucket and stops at the first bucket that has an empty cell. */
+#define ACM_QSET_EMPTY 0xFFFFFFFFu
 ACM_HD uint32_t
-acm_qslot_hash (uint32_t key, uint32_t shift) {
-  return (key * 0x9E3779B1u) >> shift; /* top bits of a multiplicative hash; slots = 1 << (32 - shift) */
+acm_qset_bucket (uint32_t key, uint32_t shift) {
+  return (key * 0x9E3779B1u) >> shift; /* top bits of a multiplicative hash; buckets = 1 << (32 - shift) */
 }
 
 typedef struct {
@@ -107,8 +106,9 @@ struct acm_tables {
   uint32_t bloom_words, bloom_k;
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
-  acm_qslot *qcompact;        /* same keys, compact form, widths 1 and 2 only */
-  uint32_t qcompact_shift;    /* slots = 1 << (32 - shift) */
+  uint32_t *qset;             /* same keys as a compact set (4 keys per 16-byte bucket), widths 1 and 2 only */
+  uint32_t qset_shift;        /* buckets = 1 << (32 - shift) */
+  uint32_t qset_has_empty_key;
   acm_slot *edges;
   uint64_t edge_slots;        /* power of two */
   uint32_t nb_rev_nodes;
