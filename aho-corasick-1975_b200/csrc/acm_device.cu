@@ -205,6 +205,7 @@ finalise_locked (ACMachine *m, int device) {
   s.min_keyword_length = t.lmin;
   s.nb_classes = t.nb_classes;
   s.table_bytes = bytes;
+  s.filter_fp = t.engine == ACM_B200_ENGINE_FILTER ? t.bloom_fp : 0;
   s.finalise_count++;
   s.finalise_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count ();
   return ACM_B200_OK;
@@ -386,7 +387,9 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.edge_mask = t.edge_slots - 1;
     p.prefix = d_small->prefix;
     p.prefix_len = job.prefix_len;
-    p.stage_cap = dense ? p.tile_syms : 192;
+    /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */
+    const uint32_t expected_hits = (uint32_t)(t.bloom_fp * p.tile_syms);
+    p.stage_cap = dense ? p.tile_syms : std::min<uint32_t> (p.tile_syms, std::max<uint32_t> (192, 2 * expected_hits + 128));
     p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / 32, 1u << 16);
     size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
     int warps = 32;

@@ -376,6 +376,12 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     uint32_t f = acm_fold_key (qkeys[i]);
     t->bloom[acm_bloom_word (f, t->bloom_words)] |= acm_bloom_mask (f, t->bloom_k);
   }
+  double fp = 0;
+  for (uint32_t i = 0; i < t->bloom_words; i++) {
+    const double f = __builtin_popcount (t->bloom[i]) / 32.0;
+    fp += t->bloom_k > 2 ? f * f * f : f * f;
+  }
+  t->bloom_fp = fp / t->bloom_words;
   free (qkeys);
   free (qnodes);
   return ACM_B200_OK;

@@ -104,6 +104,7 @@ struct acm_tables {
   uint32_t q;                 /* symbols per filter window = min(lmin, 4 for bytes / 2 otherwise) */
   uint32_t *bloom;
   uint32_t bloom_words, bloom_k;
+  double bloom_fp;            /* expected false-positive rate of one probe, from the actual fill of every word */
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
   uint32_t *qset;             /* same keys as a compact set (4 keys per 16-byte bucket), widths 1 and 2 only */

@@ -78,7 +78,8 @@ typedef struct {
   double h2d_ms, d2h_ms;
   uint64_t last_nb_symbols, last_nb_matches, last_nb_candidates;
   uint64_t main_kernel_launches, total_kernel_launches; /* since machine creation */
-  uint64_t fallback_count;  /* scans re-run on the DFA engine because the filter engine's candidate buffers overflowed */
+  uint64_t fallback_count;  /* scans re-run in the filter engine's dense mode because a candidate buffer overflowed */
+  double filter_fp;         /* expected false-positive rate of the shared-memory filter (0 for the DFA engines) */
 } ACMB200Stats;
 
 /* Number of CUDA devices visible (0 if none / no driver). */

@@ -1,0 +1,128 @@
+"""GPU parity at the shapes of BASELINE.json configs[3], configs[4] and at configs[2]'s full size.
+
+Sizes the oracle finishes in seconds are compared record for record; the full-size run is checked through size-independent
+properties (exact prefix, recall of every sampled planted keyword, shards summing to the whole, engines agreeing)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import ac75, random_patterns
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def zipf_tokens(n, vocab, seed):
+    """Zipf(1.0) over `vocab` ids via the inverse CDF."""
+    rng = np.random.default_rng(seed)
+    cdf = np.cumsum(1.0 / np.arange(1, vocab + 1))
+    cdf /= cdf[-1]
+    return np.searchsorted(cdf, rng.random(n)).astype(np.uint32)
+
+
+def test_config5_token_ngrams_incremental_meyer():
+    """uint32 alphabet, 50k-symbol vocabulary, n-gram keywords cut from the stream (so they occur, densely for frequent tokens),
+    then rounds of insertions each followed by a scan of the next slice with the cursor carried: every round is one DFA/filter
+    rebuild + re-upload, and the result must equal the reference-semantics oracle's carried-cursor scan."""
+    vocab, n, rounds = 50_000, 1_200_000, 6
+    stream = zipf_tokens(n, vocab, 42)
+    rng = np.random.default_rng(43)
+
+    def cut(k):
+        starts, lens = rng.integers(0, n - 8, size=k), rng.integers(2, 9, size=k)
+        flat = np.concatenate([stream[a:a + l] for a, l in zip(starts, lens)])
+        return flat, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+
+    o = pyoracle.Oracle("port", 4)
+    m = ac75().Machine(4)
+    flat, offsets = cut(20_000)
+    assert np.array_equal(o.insert_many(flat=flat, offsets=offsets), m.insert_many(flat=flat, offsets=offsets))
+    per = n // (rounds + 1)
+    total = 0
+    for r in range(rounds + 1):
+        if r:
+            flat, offsets = cut(200)  # Meyer phase: a few insertions between two scans
+            assert np.array_equal(o.insert_many(flat=flat, offsets=offsets), m.insert_many(flat=flat, offsets=offsets))
+        sl = stream[r * per:(r + 1) * per]
+        want = o.scan(sl, base=r * per, cap=1 << 24)
+        got = m.scan(sl, base=r * per, carry=True, capacity=1 << 24)
+        assert len(want) > 1000 and np.array_equal(got, want), (r, len(got), len(want))
+        total += len(got)
+    st = m.stats()
+    assert st["engine"] == "filter" and st["symbol_width"] == 4 and st["finalise_count"] == rounds + 1
+    m.close(), o.close()
+
+
+def test_config4_shape_large_dictionary():
+    """configs[3] shape at test scale: a dictionary whose tables exceed shared memory by far (300k patterns, ~5M states)."""
+    flat, offsets = random_patterns(300_000, seed=4)
+    text = ac75().generate_text(16 << 20, kind=0, plant_period=2048, dict_flat=flat, dict_offsets=offsets)
+    o = pyoracle.Oracle("port", 1)
+    o.insert_many(flat=flat, offsets=offsets)
+    want = o.scan(text, cap=1 << 22)
+    m = ac75().Machine(1)
+    m.insert_many(flat=flat, offsets=offsets)
+    got = m.scan(text, capacity=1 << 22)
+    st = m.stats()
+    assert st["engine"] == "filter" and st["nb_states"] > 4_000_000 and st["fallback_count"] == 0
+    assert len(want) >= 8000 and np.array_equal(got, want)
+    m.close(), o.close()
+
+
+@pytest.mark.slow
+def test_config3_full_size_properties():
+    """configs[2] at its full size (100k patterns, 8 GiB on one GPU), device-resident."""
+    import torch
+
+    flat, offsets = random_patterns(100_000, seed=0xD1C7)
+    n = 8 << 30
+    m = ac75().Machine(1)
+    ids = m.insert_many(flat=flat, offsets=offsets)
+    d_text = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+    ac75().generate_text(n, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets, device_ptr=d_text.data_ptr())
+    cap = 1 << 22
+    d_out = torch.empty(cap * 16, dtype=torch.uint8, device="cuda")
+    total = m.scan_device(d_text.data_ptr(), n, d_matches_ptr=d_out.data_ptr(), capacity=cap)
+    assert m.stats()["engine"] == "filter" and m.stats()["fallback_count"] == 0 and total <= cap
+    recs = d_out[: total * 16].cpu().numpy().view(ac75().MATCH_DTYPE)
+    # (1) the reference's emission order: end ascending, longest first
+    assert np.array_equal(pyoracle.sort_records(recs), recs)
+    # (2) exact equality with the oracle on a 32 MiB prefix
+    pre = 32 << 20
+    host_prefix = d_text[:pre].cpu().numpy()
+    o = pyoracle.Oracle("port", 1)
+    o.insert_many(flat=flat, offsets=offsets)
+    want = o.scan(host_prefix, cap=1 << 20)
+    got_prefix = recs[recs["end"] < pre]
+    assert len(want) > 8000 and np.array_equal(got_prefix, want)
+    # (3) recall: the keyword planted in sampled 4 KiB periods is reported at its position (generator of acm_kernels.cuh::gen_byte)
+    def mix64(x):
+        x = np.uint64(x)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    rng = np.random.default_rng(1)
+    ends = recs["end"]
+    checked = 0
+    with np.errstate(over="ignore"):
+        for b in rng.integers(1, (n // 4096) - 1, size=4000):
+            r = mix64(np.uint64(0x5EED) + np.uint64(b) * np.uint64(0x9E3779B97F4A7C15))
+            kw, at = int((r >> np.uint64(20)) % np.uint64(len(ids))), int((r & np.uint64(0xFFFFF)) % np.uint64(4096))
+            length = int(offsets[kw + 1] - offsets[kw])
+            r2 = mix64(np.uint64(0x5EED) + np.uint64(b + 1) * np.uint64(0x9E3779B97F4A7C15))
+            at2 = int((r2 & np.uint64(0xFFFFF)) % np.uint64(4096))
+            if at + length > 4096 + at2:  # overwritten by the next period's plant
+                continue
+            end = int(b) * 4096 + at + length - 1
+            lo, hi = np.searchsorted(ends, end, "left"), np.searchsorted(ends, end, "right")
+            assert any(int(x["id"]) == int(ids[kw]) and int(x["len"]) == length for x in recs[lo:hi]), (b, kw, end)
+            checked += 1
+    assert checked > 3000
+    # (4) shards with leads sum to the whole and reproduce it
+    parts, lmax = [], m.max_keyword_length
+    for (a, bnd, lead) in ac75().plan_shards(n, 8, lmax):
+        k = m.scan_device(d_text.data_ptr() + a - lead, bnd - a + lead, lead=lead, base=a - lead, d_matches_ptr=d_out.data_ptr(), capacity=cap)
+        parts.append(d_out[: k * 16].cpu().numpy().view(ac75().MATCH_DTYPE).copy())
+    assert sum(len(p) for p in parts) == total and np.array_equal(np.concatenate(parts), recs)
+    m.close(), o.close()
