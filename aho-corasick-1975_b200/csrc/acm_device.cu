@@ -88,7 +88,7 @@ struct acm_device_image {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qset, d_edges;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
   DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
@@ -105,7 +105,7 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_text, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
@@ -177,9 +177,12 @@ finalise_locked (ACMachine *m, int device) {
   if (t.engine == ACM_B200_ENGINE_FILTER) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
         || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
-        || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st))))
+        || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
+        || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
+        || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st)))
       return rc;
-    bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot);
+    bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot) + t.kw_pool_bytes + (uint64_t)t.nb_keywords * 12
+            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0);
   } else {
     if ((rc = upload (img->d_delta, t.delta, t.delta_bytes, st)) || (rc = upload (img->d_out_offsets, t.out_offsets, ((size_t)t.nb_dfa_states - t.out_threshold + 1) * 4, st))
         || (rc = upload (img->d_out_entries, t.out_entries, t.nb_out_entries * sizeof (acm_output), st)))
@@ -194,6 +197,9 @@ finalise_locked (ACMachine *m, int device) {
   free (t.bloom), t.bloom = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
   free (t.qset), t.qset = nullptr;
+  free (t.kw_len), t.kw_len = nullptr;
+  free (t.kw_off), t.kw_off = nullptr;
+  free (t.kw_pool), t.kw_pool = nullptr;
   free (t.edges), t.edges = nullptr;
   m->device_generation = m->generation;
   ACMB200Stats &s = img->stats;
@@ -362,7 +368,8 @@ template <int W>
 static int
 run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
   const acm_tables &t = img->tab;
-  constexpr int kRows = 4;
+  constexpr int kPasses = 1;
+  const int kRowsOpt = m->option_tile_rows == 2 ? 2 : 4; /* rows of 512 bytes per warp tile (tuning knob) */
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
   for (int attempt = 0; attempt < 2; attempt++) {
     const bool dense = attempt == 1; /* second try: no candidate buffer can overflow */
@@ -372,8 +379,8 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.lead = job.lead;
     p.base = job.base;
     p.q = t.q;
-    p.tile_rows = kRows;
-    p.tile_syms = kRows * 512 / W;
+    p.tile_rows = kRowsOpt;
+    p.tile_syms = kRowsOpt * kPasses * 512 / W;
     p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
     p.bloom = img->d_bloom.as<uint32_t> ();
     p.bloom_words = t.bloom_words;
@@ -385,6 +392,9 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.qset_has_empty_key = t.qset_has_empty_key;
     p.edges = img->d_edges.as<acm_slot> ();
     p.edge_mask = t.edge_slots - 1;
+    p.kw_len = img->d_kw_len.as<uint32_t> ();
+    p.kw_off = img->d_kw_off.as<uint64_t> ();
+    p.kw_pool = img->d_kw_pool.ptr;
     p.prefix = d_small->prefix;
     p.prefix_len = job.prefix_len;
     /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */
@@ -416,7 +426,10 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     void (*f1) (const FilterParams) = nullptr;
     const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
     const int K = t.bloom_k > 2 ? 3 : 2;
-#define ACM_F1(Q_, K_) if (p.q == Q_ && K == K_) f1 = ordered ? filter_scan_kernel<W, kRows, Q_, K_, true> : filter_scan_kernel<W, kRows, Q_, K_, false>
+#define ACM_F1(Q_, K_)                                                                                                                          \
+  if (p.q == Q_ && K == K_)                                                                                                                     \
+    f1 = kRowsOpt == 2 ? (ordered ? filter_scan_kernel<W, 2, kPasses, Q_, K_, true> : filter_scan_kernel<W, 2, kPasses, Q_, K_, false>)         \
+                       : (ordered ? filter_scan_kernel<W, 4, kPasses, Q_, K_, true> : filter_scan_kernel<W, 4, kPasses, Q_, K_, false>)
     ACM_F1 (1, 2); ACM_F1 (1, 3); ACM_F1 (2, 2); ACM_F1 (2, 3);
     if (W == 1) {
       ACM_F1 (3, 2); ACM_F1 (3, 3); ACM_F1 (4, 2); ACM_F1 (4, 3);

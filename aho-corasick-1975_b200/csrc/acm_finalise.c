@@ -160,6 +160,9 @@ acm_free_tables (struct acm_tables *t) {
   free (t->bloom);
   free (t->qgrams);
   free (t->qset);
+  free (t->kw_len);
+  free (t->kw_off);
+  free (t->kw_pool);
   free (t->edges);
   memset (t, 0, sizeof (*t));
 }
@@ -253,6 +256,9 @@ build_dfa (struct _ac_machine *m, struct acm_tables *t, struct _ac_state **by_de
 }
 
 /* ---- filter engine -------------------------------------------------------------------------------------------------- */
+/* Reverse trie (keywords read right to left), path-compressed: an edge whose subtree holds exactly ONE keyword does not lead to a
+ * node but to a "tail" (ACM_TAIL_FLAG | keyword id): the rest of that keyword is compared directly against the text from the
+ * keyword pool.  Only edges leaving nodes with two or more keywords below them are stored. */
 static int
 build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget) {
   const uint32_t nk = (uint32_t)m->nb_sequences;
@@ -263,75 +269,124 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
   uint32_t qmax = t->width == 1 ? 4 : 2;
   if (t->q > qmax)
     t->q = qmax;
-  /* reverse trie in an edge hash table; node 0 = root */
-  t->edge_slots = pow2_at_least (2 * total_syms + 16);
-  t->edges = malloc (t->edge_slots * sizeof (acm_slot));
-  if (!t->edges)
-    return ACM_B200_ERR_NOMEM;
-  memset (t->edges, 0xFF, t->edge_slots * sizeof (acm_slot));
-  uint32_t nodes = 1;
-  uint64_t nq = 0; /* distinct depth-q nodes */
-  /* first pass: build nodes; remember, for every depth-q node, its packed key */
-  uint64_t cap_q = 1024;
+  const uint32_t q = t->q;
+  const int shift = t->width == 1 ? 8 : (t->width == 2 ? 16 : 32);
+  int rc = ACM_B200_ERR_NOMEM;
+
+  /* keyword pool (forward symbols) for the tail compares */
+  t->kw_len = malloc (((size_t)nk + 1) * sizeof (uint32_t));
+  t->kw_off = malloc (((size_t)nk + 1) * sizeof (uint64_t));
+  t->kw_pool_bytes = (total_syms + 4) * (uint64_t)t->width;
+  t->kw_pool = calloc (1, t->kw_pool_bytes);
+  /* full (uncompressed) reverse trie, host only */
+  const uint64_t full_slots = pow2_at_least (2 * total_syms + 16);
+  acm_slot *full = malloc (full_slots * sizeof (acm_slot));
+  const size_t max_nodes = (size_t)total_syms + 2;
+  uint32_t *parent = malloc (max_nodes * sizeof (uint32_t)), *depth = malloc (max_nodes * sizeof (uint32_t));
+  uint32_t *count = calloc (max_nodes, sizeof (uint32_t)), *only_kw = malloc (max_nodes * sizeof (uint32_t));
+  uint32_t *term_kw = malloc (max_nodes * sizeof (uint32_t));
+  uint64_t cap_q = 1024, nq = 0;
   uint64_t *qkeys = malloc (cap_q * sizeof (*qkeys));
   uint32_t *qnodes = malloc (cap_q * sizeof (*qnodes));
-  if (!qkeys || !qnodes)
-    return ACM_B200_ERR_NOMEM;
-  const int shift = t->width == 1 ? 8 : (t->width == 2 ? 16 : 32);
+  if (!t->kw_len || !t->kw_off || !t->kw_pool || !full || !parent || !depth || !count || !only_kw || !term_kw || !qkeys || !qnodes)
+    goto done;
+  memset (full, 0xFF, full_slots * sizeof (acm_slot));
+  memset (term_kw, 0xFF, max_nodes * sizeof (uint32_t));
+  uint32_t nodes = 1;
+  parent[0] = 0;
+  depth[0] = 0;
+  uint64_t pool_at = 0;
   for (uint32_t r = 0; r < nk; r++) {
-    uint32_t node = 0, depth = 0;
+    const uint32_t len = m->keywords[r]->depth;
+    t->kw_len[r] = len;
+    t->kw_off[r] = pool_at;
+    uint32_t node = 0, d = 0;
     uint64_t key = 0;
     for (const struct _ac_state *s = m->keywords[r]; s->parent; s = s->parent) { /* last letter first */
-      uint32_t sym = acm_symbol_of_state (m, s);
-      uint64_t ekey = ((uint64_t)node << 32) | sym;
-      acm_slot *e = slot_find (t->edges, t->edge_slots, ekey);
+      const uint32_t sym = acm_symbol_of_state (m, s);
+      const uint64_t at = pool_at + (len - 1 - d);
+      if (t->width == 1)
+        ((uint8_t *)t->kw_pool)[at] = (uint8_t)sym;
+      else if (t->width == 2)
+        ((uint16_t *)t->kw_pool)[at] = (uint16_t)sym;
+      else
+        ((uint32_t *)t->kw_pool)[at] = sym;
+      const uint64_t ekey = ((uint64_t)node << 32) | sym;
+      acm_slot *e = slot_find (full, full_slots, ekey);
       int created = 0;
       if (!e) {
-        slot_insert (t->edges, t->edge_slots, ekey, nodes++, ACM_TAB_NONE);
-        e = slot_find (t->edges, t->edge_slots, ekey);
+        parent[nodes] = node;
+        depth[nodes] = d + 1;
+        slot_insert (full, full_slots, ekey, nodes++, ACM_TAB_NONE);
+        e = slot_find (full, full_slots, ekey);
         created = 1;
       }
       node = e->node;
-      depth++;
-      if (depth <= t->q) {
-        key = shift == 32 ? ((depth == 1 ? 0 : key << 32) | sym) : ((key << shift) | sym);
-        if (depth == t->q && created) {
+      d++;
+      if (d <= q) {
+        key = shift == 32 ? ((d == 1 ? 0 : key << 32) | sym) : ((key << shift) | sym);
+        if (d == q && created) {
           if (nq == cap_q) {
             cap_q *= 2;
             qkeys = realloc (qkeys, cap_q * sizeof (*qkeys));
             qnodes = realloc (qnodes, cap_q * sizeof (*qnodes));
             if (!qkeys || !qnodes)
-              return ACM_B200_ERR_NOMEM;
+              goto done;
           }
           qkeys[nq] = key;
           qnodes[nq++] = node;
         }
       }
-      if (!s->parent->parent) /* s is the first letter of the keyword: the reversed keyword ends at `node` */
-        e->keyword = r;
     }
+    term_kw[node] = r; /* distinct keywords end at distinct nodes */
+    pool_at += len;
   }
   t->nb_rev_nodes = nodes;
-  /* exact q-gram table; the keyword field tells whether a keyword of exactly q symbols ends at that node */
+  /* keywords per subtree; children have larger ids than their parent */
+  for (uint32_t v = nodes - 1; v >= 1; v--) {
+    if (term_kw[v] != ACM_TAB_NONE) {
+      count[v]++;
+      only_kw[v] = term_kw[v];
+    }
+    count[parent[v]] += count[v];
+    only_kw[parent[v]] = only_kw[v]; /* meaningful only where the final count is 1 */
+  }
+  /* stored edges: those leaving a node at depth >= q that has >= 2 keywords below it */
+  uint64_t kept = 0;
+  for (uint64_t i = 0; i < full_slots; i++)
+    if (full[i].node != ACM_TAB_NONE) {
+      const uint32_t from = (uint32_t)(full[i].key >> 32);
+      if (depth[from] >= q && count[from] >= 2)
+        kept++;
+    }
+  t->edge_slots = pow2_at_least (2 * kept + 16);
+  t->edges = malloc (t->edge_slots * sizeof (acm_slot));
+  if (!t->edges)
+    goto done;
+  memset (t->edges, 0xFF, t->edge_slots * sizeof (acm_slot));
+  for (uint64_t i = 0; i < full_slots; i++)
+    if (full[i].node != ACM_TAB_NONE) {
+      const uint32_t from = (uint32_t)(full[i].key >> 32), to = full[i].node;
+      if (depth[from] >= q && count[from] >= 2) {
+        if (count[to] == 1)
+          slot_insert (t->edges, t->edge_slots, full[i].key, ACM_TAIL_FLAG | only_kw[to], ACM_TAB_NONE);
+        else
+          slot_insert (t->edges, t->edge_slots, full[i].key, to, term_kw[to]);
+      }
+    }
+  /* exact q-gram table: depth-q node (or tail), and the keyword of exactly q symbols ending there */
   t->qgram_slots = pow2_at_least (2 * nq + 16);
   t->qgrams = malloc (t->qgram_slots * sizeof (acm_slot));
   if (!t->qgrams)
-    return ACM_B200_ERR_NOMEM;
+    goto done;
   memset (t->qgrams, 0xFF, t->qgram_slots * sizeof (acm_slot));
-  /* node -> keyword for depth-q nodes: look the edge up again through the keyword walk (cheap: reuse edge slots) */
-  for (uint64_t i = 0; i < nq; i++)
-    slot_insert (t->qgrams, t->qgram_slots, qkeys[i], qnodes[i], ACM_TAB_NONE);
-  for (uint32_t r = 0; r < nk; r++)
-    if (m->keywords[r]->depth == t->q) { /* keyword of exactly q symbols */
-      uint64_t key = 0;
-      uint32_t depth = 0;
-      for (const struct _ac_state *s = m->keywords[r]; s->parent; s = s->parent) {
-        uint32_t sym = acm_symbol_of_state (m, s);
-        depth++;
-        key = shift == 32 ? ((depth == 1 ? 0 : key << 32) | sym) : ((key << shift) | sym);
-      }
-      slot_find (t->qgrams, t->qgram_slots, key)->keyword = r;
-    }
+  for (uint64_t i = 0; i < nq; i++) {
+    const uint32_t v = qnodes[i];
+    if (count[v] == 1)
+      slot_insert (t->qgrams, t->qgram_slots, qkeys[i], ACM_TAIL_FLAG | only_kw[v], ACM_TAB_NONE);
+    else
+      slot_insert (t->qgrams, t->qgram_slots, qkeys[i], v, term_kw[v]);
+  }
   if (t->width != 4) { /* compact confirmation set, load factor <= 1/4 */
     uint32_t bits = 8;
     while ((4ull << bits) < 4 * nq + 16 && bits < 29)
@@ -339,7 +394,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     t->qset_shift = 32 - bits;
     t->qset = malloc ((size_t)16 << bits);
     if (!t->qset)
-      return ACM_B200_ERR_NOMEM;
+      goto done;
     memset (t->qset, 0xFF, (size_t)16 << bits);
     const uint32_t mask = (1u << bits) - 1u;
     for (uint64_t i = 0; i < nq; i++) {
@@ -371,7 +426,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     t->bloom_k = 2;
   t->bloom = calloc (t->bloom_words, sizeof (uint32_t));
   if (!t->bloom)
-    return ACM_B200_ERR_NOMEM;
+    goto done;
   for (uint64_t i = 0; i < nq; i++) {
     uint32_t f = acm_fold_key (qkeys[i]);
     t->bloom[acm_bloom_word (f, t->bloom_words)] |= acm_bloom_mask (f, t->bloom_k);
@@ -382,9 +437,17 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     fp += t->bloom_k > 2 ? f * f * f : f * f;
   }
   t->bloom_fp = fp / t->bloom_words;
+  rc = ACM_B200_OK;
+done:
+  free (full);
+  free (parent);
+  free (depth);
+  free (count);
+  free (only_kw);
+  free (term_kw);
   free (qkeys);
   free (qnodes);
-  return ACM_B200_OK;
+  return rc;
 }
 
 /* ---- entry ---------------------------------------------------------------------------------------------------------- */

@@ -218,6 +218,9 @@ struct FilterParams {
   uint32_t qset_shift, qset_has_empty_key;
   const acm_slot *edges;
   uint64_t edge_mask;
+  const uint32_t *kw_len; /* tails: keyword id -> length, first symbol in the pool, the pool (forward symbols) */
+  const uint64_t *kw_off;
+  const void *kw_pool;
   const uint32_t *prefix; /* symbols virtually preceding the text (carried cursor), prefix_len of them */
   uint32_t prefix_len;
   uint32_t stage_cap; /* raw hits a warp can stage per tile */
@@ -348,7 +351,7 @@ qset_contains (const FilterParams &p, uint32_t key) {
  * kOrdered: raw hits are staged in position order with a warp scan (used by the dense fallback, where a tile may hold thousands
  * of candidates); otherwise they are staged through a shared-memory counter in any order and the few survivors of the exact
  * confirmation are sorted afterwards -- fewer instructions when hits are rare. */
-template <int W, int kRows, int Q, int K, bool kOrdered>
+template <int W, int kRows, int kPasses, int Q, int K, bool kOrdered>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -365,7 +368,8 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   uint16_t *stage = reinterpret_cast<uint16_t *> (stage_count + 4);
   constexpr int kSyms = 16 / W;        /* symbols per lane per row */
   constexpr int kRowSyms = 32 * kSyms; /* symbols per row */
-  constexpr uint32_t kTileSyms = kRows * kRowSyms;
+  constexpr uint32_t kPassSyms = kRows * kRowSyms;    /* symbols filtered per pass (kRows loads in flight per lane) */
+  constexpr uint32_t kTileSyms = kPasses * kPassSyms; /* a tile = kPasses passes sharing one staging / confirmation / reservation */
   constexpr uint32_t q = Q;
   const uint32_t nwords = p.bloom_words, stage_cap = p.stage_cap;
   const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
@@ -377,7 +381,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
     uint32_t staged = 0; /* warp-uniform */
     { /* pull this warp's next tile from DRAM into L2 while the current one is being processed */
       const uint64_t next = tile + (uint64_t)gridDim.x * warps;
-      if (next < p.ntiles && lane < kRows * 4)
+      if (next < p.ntiles && lane < kRows * kPasses * 4)
         asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + next * (kTileSyms * W) + lane * 128));
     }
     /* interior tiles (every symbol reportable, every vector load inside the text) take the check-free path */
@@ -399,16 +403,19 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       __syncwarp ();
     }
 
-    /* all rows of the tile are requested up front: kRows independent 16-byte loads per lane in flight */
+    for (int pass = 0; pass < kPasses; pass++) {
+    const uint64_t pass_base = tile_base + (uint64_t)pass * kPassSyms;
+    const uint8_t *pass_ptr = tile_ptr + (size_t)pass * kPassSyms * W;
+    /* all rows of the pass are requested up front: kRows independent 16-byte loads per lane in flight */
     uint4 v[kRows];
     if (interior) {
 #pragma unroll
       for (int r = 0; r < kRows; r++)
-        v[r] = *reinterpret_cast<const uint4 *> (tile_ptr + r * 512 + lane * 16);
+        v[r] = *reinterpret_cast<const uint4 *> (pass_ptr + r * 512 + lane * 16);
     } else {
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
-        const uint64_t byte0 = (tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms) * W, nbytes = p.n * W;
+        const uint64_t byte0 = (pass_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms) * W, nbytes = p.n * W;
         if (byte0 + 16 <= nbytes)
           v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
         else {
@@ -420,7 +427,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         }
       }
     }
-    const uint32_t before_tile = tile_base * W >= 4 ? *reinterpret_cast<const uint32_t *> (tile_ptr - 4) : 0;
+    const uint32_t before_tile = pass_base * W >= 4 ? *reinterpret_cast<const uint32_t *> (pass_ptr - 4) : 0;
 
     uint32_t hits[kRows];
 #pragma unroll
@@ -433,7 +440,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
     if (!interior) { /* drop positions outside [first_valid, n) */
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
-        const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
+        const uint64_t pos0 = pass_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
         uint32_t keep = 0;
         for (int i = 0; i < kSyms; i++)
           if (pos0 + i >= first_valid && pos0 + i < p.n)
@@ -465,7 +472,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         const uint32_t total = __shfl_sync (kFull, mine, 31);
         uint32_t at = row_start + mine - __popc (hits[r]);
         uint32_t h = hits[r];
-        const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
+        const uint32_t rel0 = (uint32_t)(pass * kPassSyms + r * kRowSyms + lane * kSyms);
         while (h) {
           const int i = __ffs (h) - 1;
           h &= h - 1;
@@ -488,7 +495,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
           uint32_t h = hits[r];
-          const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
+          const uint32_t rel0 = (uint32_t)(pass * kPassSyms + r * kRowSyms + lane * kSyms);
           while (h) {
             const int i = __ffs (h) - 1;
             h &= h - 1;
@@ -498,6 +505,9 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
           }
         }
       }
+    }
+    } /* passes */
+    if (!kOrdered) {
       __syncwarp ();
       staged = *stage_count;
     }
@@ -637,23 +647,38 @@ filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candid
   uint4 first_two = make_uint4 (0, 0, 0, 0);
   uint64_t key;
   uint32_t node, kw, found = 0;
+  auto report = [&] (uint32_t keyword, uint32_t len) {
+    if (kEmit) { /* found shortest first; the record order is longest first */
+      const uint64_t at = out + (expected - 1 - found);
+      if (at < p.capacity)
+        p.matches[at] = ACMB200Match{ p.base + (uint64_t)pos, keyword, len };
+    } else if (found == 0) {
+      first_two.x = keyword;
+      first_two.y = len;
+    } else if (found == 1) {
+      first_two.z = keyword;
+      first_two.w = len;
+    }
+    found++;
+  };
   if (qgram_key_at<W> (p, pos, &key) && slot_lookup (p.qgrams, p.qgram_mask, key, &node, &kw)) {
     uint32_t len = p.q;
     for (;;) {
-      if (kw != ACM_TAB_NONE) {
-        if (kEmit) { /* found shortest first; the record order is longest first */
-          const uint64_t at = out + (expected - 1 - found);
-          if (at < p.capacity)
-            p.matches[at] = ACMB200Match{ p.base + (uint64_t)pos, kw, len };
-        } else if (found == 0) {
-          first_two.x = kw;
-          first_two.y = len;
-        } else if (found == 1) {
-          first_two.z = kw;
-          first_two.w = len;
+      if (node != ACM_TAB_NONE && (node & ACM_TAIL_FLAG)) {
+        /* exactly one keyword lies below: compare its remaining symbols with the text, right to left */
+        const uint32_t k = node & ~ACM_TAIL_FLAG, klen = p.kw_len[k];
+        const typename SymT<W>::type *kwsym = reinterpret_cast<const typename SymT<W>::type *> (p.kw_pool) + p.kw_off[k];
+        bool same = true;
+        for (uint32_t j = len; j < klen && same; j++) {
+          uint32_t sym;
+          same = symbol_at<W> (p, pos - (int64_t)j, &sym) && sym == kwsym[klen - 1 - j];
         }
-        found++;
+        if (same)
+          report (k, klen);
+        break;
       }
+      if (kw != ACM_TAB_NONE)
+        report (kw, len);
       uint32_t sym;
       if (!symbol_at<W> (p, pos - (int64_t)len, &sym))
         break;

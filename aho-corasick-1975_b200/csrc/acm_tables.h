@@ -68,6 +68,8 @@ typedef struct {
   uint32_t keyword;
 } acm_slot;
 #define ACM_TAB_NONE 0xFFFFFFFFu
+/* node field of a slot: this flag + keyword id = "only that keyword lies below: compare its remaining symbols directly" */
+#define ACM_TAIL_FLAG 0x80000000u
 
 /* Compact q-gram key set for keys that fit 32 bits (byte and 16-bit alphabets), used by the confirmation step of the filter kernel:
  * buckets of 4 keys (16 bytes = one vector load); a key lives in its home bucket or, if that is full, in the next ones.
@@ -113,6 +115,10 @@ struct acm_tables {
   acm_slot *edges;
   uint64_t edge_slots;        /* power of two */
   uint32_t nb_rev_nodes;
+  uint32_t *kw_len;           /* keyword id -> length in symbols */
+  uint64_t *kw_off;           /* keyword id -> first symbol in kw_pool */
+  void *kw_pool;              /* every keyword's symbols, forward, `width` bytes each */
+  uint64_t kw_pool_bytes;
 };
 
 #ifdef __cplusplus
