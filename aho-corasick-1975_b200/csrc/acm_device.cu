@@ -88,7 +88,7 @@ struct acm_device_image {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
   DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
@@ -97,6 +97,7 @@ struct acm_device_image {
     uint32_t pad;
     uint32_t prefix[1024];
   } *h_small = nullptr;
+  bool two_level = false; /* the filter engine uses the second-level filter in global memory */
   ACMB200Stats stats = {};
 };
 
@@ -105,7 +106,7 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
@@ -175,7 +176,7 @@ finalise_locked (ACMachine *m, int device) {
   cudaStream_t st = img->stream;
   uint64_t bytes = 0;
   if (t.engine == ACM_B200_ENGINE_FILTER) {
-    if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
+    if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (t.bloom2 && (rc = upload (img->d_bloom2, t.bloom2, (size_t)t.bloom2_words * 4, st))) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
         || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
         || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
         || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
@@ -195,6 +196,8 @@ finalise_locked (ACMachine *m, int device) {
   free (t.out_offsets), t.out_offsets = nullptr;
   free (t.out_entries), t.out_entries = nullptr;
   free (t.bloom), t.bloom = nullptr;
+  img->two_level = t.bloom2 != nullptr;
+  free (t.bloom2), t.bloom2 = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
   free (t.qset), t.qset = nullptr;
   free (t.kw_len), t.kw_len = nullptr;
@@ -385,6 +388,8 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     p.bloom = img->d_bloom.as<uint32_t> ();
     p.bloom_words = t.bloom_words;
     p.bloom_k = t.bloom_k;
+    p.bloom2 = img->two_level ? img->d_bloom2.as<uint32_t> () : nullptr;
+    p.bloom2_words = t.bloom2_words;
     p.qgrams = img->d_qgrams.as<acm_slot> ();
     p.qgram_mask = t.qgram_slots - 1;
     p.qset = W == 4 ? nullptr : img->d_qset.as<uint4> ();
@@ -426,15 +431,18 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     void (*f1) (const FilterParams) = nullptr;
     const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
     const int K = t.bloom_k > 2 ? 3 : 2;
-#define ACM_F1(Q_, K_)                                                                                                                          \
-  if (p.q == Q_ && K == K_)                                                                                                                     \
-    f1 = kRowsOpt == 2 ? (ordered ? filter_scan_kernel<W, 2, kPasses, Q_, K_, true> : filter_scan_kernel<W, 2, kPasses, Q_, K_, false>)         \
-                       : (ordered ? filter_scan_kernel<W, 4, kPasses, Q_, K_, true> : filter_scan_kernel<W, 4, kPasses, Q_, K_, false>)
+#define ACM_F1_(Q_, K_, R_)                                                                                                                      \
+  (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, kPasses, Q_, K_, true, true> : filter_scan_kernel<W, R_, kPasses, Q_, K_, false, true>)       \
+            : (ordered ? filter_scan_kernel<W, R_, kPasses, Q_, K_, true, false> : filter_scan_kernel<W, R_, kPasses, Q_, K_, false, false>))
+#define ACM_F1(Q_, K_)                                                                                                                           \
+  if (p.q == Q_ && K == K_)                                                                                                                      \
+    f1 = kRowsOpt == 2 ? ACM_F1_ (Q_, K_, 2) : ACM_F1_ (Q_, K_, 4)
     ACM_F1 (1, 2); ACM_F1 (1, 3); ACM_F1 (2, 2); ACM_F1 (2, 3);
     if (W == 1) {
       ACM_F1 (3, 2); ACM_F1 (3, 3); ACM_F1 (4, 2); ACM_F1 (4, 3);
     }
 #undef ACM_F1
+#undef ACM_F1_
     if (!f1)
       return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
     CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

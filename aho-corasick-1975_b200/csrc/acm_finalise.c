@@ -158,6 +158,7 @@ acm_free_tables (struct acm_tables *t) {
   free (t->out_entries);
   free (t->dfa_of_state);
   free (t->bloom);
+  free (t->bloom2);
   free (t->qgrams);
   free (t->qset);
   free (t->kw_len);
@@ -437,6 +438,22 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     fp += t->bloom_k > 2 ? f * f * f : f * f;
   }
   t->bloom_fp = fp / t->bloom_words;
+  if (t->bloom_fp > 0.08) { /* the shared-memory level alone would flood the confirmation step: add the global level */
+    t->bloom2_words = (uint32_t)pow2_at_least (nq < 1024 ? 1024 : nq); /* >= 32 bits per key */
+    t->bloom2 = calloc (t->bloom2_words, sizeof (uint32_t));
+    if (!t->bloom2)
+      goto done;
+    for (uint64_t i = 0; i < nq; i++) {
+      const uint32_t f = acm_fold_key (qkeys[i]);
+      t->bloom2[acm_bloom2_word (f, t->bloom2_words)] |= acm_bloom2_mask (f);
+    }
+    double fp2 = 0;
+    for (uint32_t i = 0; i < t->bloom2_words; i++) {
+      const double f = __builtin_popcount (t->bloom2[i]) / 32.0;
+      fp2 += f * f;
+    }
+    t->bloom_fp *= fp2 / t->bloom2_words;
+  }
   rc = ACM_B200_OK;
 done:
   free (full);

@@ -212,6 +212,8 @@ struct FilterParams {
   uint64_t ntiles;
   const uint32_t *bloom;
   uint32_t bloom_words, bloom_k;
+  const uint32_t *bloom2; /* optional second level in global memory */
+  uint32_t bloom2_words;
   const acm_slot *qgrams;
   uint64_t qgram_mask;
   const uint4 *qset; /* widths 1 and 2: the q-gram keys as a compact set, 4 keys per 16-byte bucket (acm_tables.h) */
@@ -294,9 +296,9 @@ slot_lookup (const acm_slot *__restrict__ tab, uint64_t mask, uint64_t key, uint
 
 /* Filter test of the 16/W symbols a lane owns in one row.  Returns a mask: bit i = symbol i passed.
  * w[0] = the 4 bytes before the lane's 16, w[1..4] = the lane's 16 bytes. */
-template <int W, int Q, int K>
+template <int W, int Q, int K, bool kTwoLevel>
 __device__ __forceinline__ uint32_t
-filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t (&w)[5]) {
+filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict__ bloom2, uint32_t nwords2, const uint32_t (&w)[5]) {
   uint32_t acc = 0; /* every test shifts its verdict in at bit 31 (one funnel shift); the first symbol ends at bit 32 - 16/W */
   auto push = [&] (uint32_t folded) {
     const unsigned long long p1 = (unsigned long long)folded * ACM_BLOOM_C1;
@@ -305,6 +307,13 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t (&w)[5]) {
     uint32_t t = (word >> (h1 & 31u)) & (word >> (h2 & 31u));
     if (K > 2)
       t &= word >> ((h2 >> 5) & 31u);
+    if (kTwoLevel) { /* survivors of the shared-memory level ask the L2-resident level */
+      uint32_t word2 = 0;
+      if (t & 1u)
+        word2 = __ldg (bloom2 + __umulhi (folded * ACM_BLOOM_C3, nwords2));
+      const uint32_t h3 = __umulhi (folded, ACM_BLOOM_C4);
+      t &= (word2 >> (h3 & 31u)) & (word2 >> ((h3 >> 5) & 31u));
+    }
     acc = __funnelshift_r (acc, t, 1); /* (acc >> 1) | (t << 31): only bit 0 of t survives */
   };
   if (W == 1) {
@@ -351,7 +360,7 @@ qset_contains (const FilterParams &p, uint32_t key) {
  * kOrdered: raw hits are staged in position order with a warp scan (used by the dense fallback, where a tile may hold thousands
  * of candidates); otherwise they are staged through a shared-memory counter in any order and the few survivors of the exact
  * confirmation are sorted afterwards -- fewer instructions when hits are rare. */
-template <int W, int kRows, int kPasses, int Q, int K, bool kOrdered>
+template <int W, int kRows, int kPasses, int Q, int K, bool kOrdered, bool kTwoLevel>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -435,7 +444,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       const uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
       const uint32_t wrap = r == 0 ? before_tile : __shfl_sync (kFull, v[r > 0 ? r - 1 : 0].w, 31);
       const uint32_t w[5] = { lane == 0 ? wrap : up, v[r].x, v[r].y, v[r].z, v[r].w };
-      hits[r] = filter_row<W, Q, K> (s_bloom, nwords, w);
+      hits[r] = filter_row<W, Q, K, kTwoLevel> (s_bloom, nwords, p.bloom2, p.bloom2_words, w);
     }
     if (!interior) { /* drop positions outside [first_valid, n) */
 #pragma unroll

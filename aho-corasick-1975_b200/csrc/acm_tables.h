@@ -58,6 +58,20 @@ acm_bloom_mask (uint32_t folded, uint32_t k) {
   return m;
 }
 
+/* Second-level filter for dictionaries too large for shared memory: same blocked layout, in global memory (L2 resident),
+ * independent hash constants, 2 bits per key, consulted only by the survivors of the shared-memory level. */
+#define ACM_BLOOM_C3 0xC2B2AE35u
+#define ACM_BLOOM_C4 0x27D4EB2Fu
+ACM_HD uint32_t
+acm_bloom2_word (uint32_t folded, uint32_t nwords) {
+  return acm_mulhi32 (folded * ACM_BLOOM_C3, nwords);
+}
+ACM_HD uint32_t
+acm_bloom2_mask (uint32_t folded) {
+  const uint32_t h = acm_mulhi32 (folded, ACM_BLOOM_C4);
+  return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+}
+
 /* One slot of the global-memory hash tables (16 bytes, read with one vector load).
  * edge table : key = (node << 32) | symbol           -> child node, keyword ending at the child (or ACM_TAB_NONE)
  * q-gram table: key = packed last q symbols of a keyword -> reverse-trie node at depth q, keyword ending there (or NONE)
@@ -106,6 +120,8 @@ struct acm_tables {
   uint32_t q;                 /* symbols per filter window = min(lmin, 4 for bytes / 2 otherwise) */
   uint32_t *bloom;
   uint32_t bloom_words, bloom_k;
+  uint32_t *bloom2;           /* optional second level in global memory (0 when the first level is selective enough) */
+  uint32_t bloom2_words;
   double bloom_fp;            /* expected false-positive rate of one probe, from the actual fill of every word */
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
