@@ -384,17 +384,53 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
   const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
 
-  for (uint64_t tile = (uint64_t)blockIdx.x * warps + warp; tile < p.ntiles; tile += (uint64_t)gridDim.x * warps) {
+  static_assert (kPasses == 1, "a tile is one pass of kRows rows");
+  /* The rows of a tile live in registers; the loads of the NEXT tile are issued right after the current tile has been filtered
+   * and staged (its rows are dead by then), so their latency hides behind the confirmation step instead of stalling the filter. */
+  uint4 v[kRows];
+  uint32_t before_tile = 0;
+  const uint64_t tile_stride = (uint64_t)gridDim.x * warps;
+  auto interior_tile = [&] (uint64_t t) { return t * kTileSyms >= first_valid + 4 && (t + 1) * kTileSyms <= p.n; };
+  auto load_tile = [&] (uint64_t t) {
+    const uint64_t base = t * kTileSyms;
+    const uint8_t *ptr = text8 + base * W;
+    if (interior_tile (t)) {
+#pragma unroll
+      for (int r = 0; r < kRows; r++)
+        v[r] = *reinterpret_cast<const uint4 *> (ptr + r * 512 + lane * 16);
+    } else {
+#pragma unroll
+      for (int r = 0; r < kRows; r++) {
+        const uint64_t byte0 = (base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms) * W, nbytes = p.n * W;
+        if (byte0 + 16 <= nbytes)
+          v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
+        else {
+          uint32_t w[4] = { 0, 0, 0, 0 };
+          for (int i = 0; i < 16; i++)
+            if (byte0 + i < nbytes)
+              w[i >> 2] |= (uint32_t)text8[byte0 + i] << (8 * (i & 3));
+          v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    before_tile = base * W >= 4 ? *reinterpret_cast<const uint32_t *> (ptr - 4) : 0;
+  };
+  {
+    const uint64_t first_tile = (uint64_t)blockIdx.x * warps + warp;
+    if (first_tile < p.ntiles)
+      load_tile (first_tile);
+  }
+
+  for (uint64_t tile = (uint64_t)blockIdx.x * warps + warp; tile < p.ntiles; tile += tile_stride) {
     const uint64_t tile_base = tile * kTileSyms; /* in symbols */
-    const uint8_t *tile_ptr = text8 + tile_base * W;
     uint32_t staged = 0; /* warp-uniform */
-    { /* pull this warp's next tile from DRAM into L2 while the current one is being processed */
-      const uint64_t next = tile + (uint64_t)gridDim.x * warps;
-      if (next < p.ntiles && lane < kRows * kPasses * 4)
-        asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + next * (kTileSyms * W) + lane * 128));
+    { /* pull the tile after the next one from DRAM into L2 */
+      const uint64_t ahead = tile + 2 * tile_stride;
+      if (ahead < p.ntiles && lane < kRows * 4)
+        asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + ahead * (kTileSyms * W) + lane * 128));
     }
     /* interior tiles (every symbol reportable, every vector load inside the text) take the check-free path */
-    const bool interior = tile_base >= first_valid + 4 && tile_base + kTileSyms <= p.n;
+    const bool interior = interior_tile (tile);
 
     /* positions whose window reaches into the carried-cursor prefix: checked exactly, by lane 0 of the first tile */
     if (tile == 0 && p.prefix_len && q > 1) {
@@ -412,32 +448,9 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       __syncwarp ();
     }
 
-    for (int pass = 0; pass < kPasses; pass++) {
-    const uint64_t pass_base = tile_base + (uint64_t)pass * kPassSyms;
-    const uint8_t *pass_ptr = tile_ptr + (size_t)pass * kPassSyms * W;
-    /* all rows of the pass are requested up front: kRows independent 16-byte loads per lane in flight */
-    uint4 v[kRows];
-    if (interior) {
-#pragma unroll
-      for (int r = 0; r < kRows; r++)
-        v[r] = *reinterpret_cast<const uint4 *> (pass_ptr + r * 512 + lane * 16);
-    } else {
-#pragma unroll
-      for (int r = 0; r < kRows; r++) {
-        const uint64_t byte0 = (pass_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms) * W, nbytes = p.n * W;
-        if (byte0 + 16 <= nbytes)
-          v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
-        else {
-          uint32_t w[4] = { 0, 0, 0, 0 };
-          for (int i = 0; i < 16; i++)
-            if (byte0 + i < nbytes)
-              w[i >> 2] |= (uint32_t)text8[byte0 + i] << (8 * (i & 3));
-          v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
-    const uint32_t before_tile = pass_base * W >= 4 ? *reinterpret_cast<const uint32_t *> (pass_ptr - 4) : 0;
-
+    {
+    constexpr int pass = 0;
+    const uint64_t pass_base = tile_base;
     uint32_t hits[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
@@ -515,7 +528,9 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         }
       }
     }
-    } /* passes */
+    } /* filter + staging */
+    if (tile + tile_stride < p.ntiles)
+      load_tile (tile + tile_stride); /* in flight during the confirmation below */
     if (!kOrdered) {
       __syncwarp ();
       staged = *stage_count;
