@@ -367,15 +367,18 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
 }
 
 /* ---- filter pipeline ------------------------------------------------------------------------------------------------ */
+enum { kFilterOverflow = 1000 }; /* internal: a candidate buffer overflowed, retry in dense mode */
+
+/* One run of the filter pipeline over job.d_text[0 .. job.n): F1, F2, F3, scan, F4.  Records go to out[0 .. out_cap). */
 template <int W>
 static int
-run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool dense, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily, uint64_t *total,
+                 ACMB200Match **out_used, bool first_segment, bool last_segment) {
   const acm_tables &t = img->tab;
   constexpr int kPasses = 1;
   const int kRowsOpt = m->option_tile_rows == 2 ? 2 : 4; /* rows of 512 bytes per warp tile (tuning knob) */
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
-  for (int attempt = 0; attempt < 2; attempt++) {
-    const bool dense = attempt == 1; /* second try: no candidate buffer can overflow */
+  {
     FilterParams p = {};
     p.text = job.d_text;
     p.n = job.n;
@@ -453,20 +456,21 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     img->h_small->overflow = 0;
     CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
     const unsigned grid = (unsigned)std::min<uint64_t> ((p.ntiles + warps - 1) / warps, (uint64_t)img->sm_count);
-    CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+    if (first_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
     f1<<<grid, warps * 32, smem, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
-    CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
+    if (first_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
     /* the number of candidates decides the grid of the verification kernels (and tells whether a buffer overflowed) */
     CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
     CUDA_TRY (cudaStreamSynchronize (job.st));
     img->stats.main_kernel_launches += 1;
     img->stats.total_kernel_launches += 1;
     if (img->h_small->overflow) {
-      img->stats.fallback_count++;
       if (dense)
         return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
-      continue;
+      return kFilterOverflow;
     }
     const uint64_t nb_cand = img->h_small->cand_count;
     const unsigned vgrid = (unsigned)((nb_cand + 255) / 256), tgrid = (unsigned)((p.ntiles + 255) / 256);
@@ -483,27 +487,72 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
     CUDA_TRY (cudaStreamSynchronize (job.st));
     *total = img->h_small->grand_total;
-    img->stats.last_nb_candidates = nb_cand;
-    const uint64_t want = std::min<uint64_t> (*total, job.capacity);
-    CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+    img->stats.last_nb_candidates += nb_cand;
+    const uint64_t want = std::min<uint64_t> (*total, out_cap);
+    if (last_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
     if (want) {
-      if (matches_on_device)
-        p.matches = user_matches;
-      else {
+      if (size_out_lazily) { /* single run into the library's own buffer: sized now that the total is known */
         if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
           return rc;
-        p.matches = img->d_matches.as<ACMB200Match> ();
+        out = img->d_matches.as<ACMB200Match> ();
       }
+      p.matches = out;
       p.capacity = want;
       filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p, nb_cand);
       CUDA_TRY (cudaGetLastError ());
       img->stats.total_kernel_launches += 1;
     }
-    CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
-    job.d_matches = p.matches;
+    if (last_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+    *out_used = out;
     return ACM_B200_OK;
   }
-  return fail (ACM_B200_ERR_CUDA, "unreachable%s", "");
+}
+
+/* Filter engine: one run over the whole text; if a candidate buffer overflows (text much denser in candidates than the filter's
+ * false-positive rate predicts), a second attempt in dense mode, where no buffer can overflow and the text is processed in bounded
+ * segments (each re-reading max depth - 1 symbols of left context) so that the scratch memory stays bounded. */
+template <int W>
+static int
+run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+  const uint64_t kDenseSegment = 64ull << 20; /* symbols */
+  img->stats.last_nb_candidates = 0;
+  ACMB200Match *used = nullptr;
+  int rc = run_filter_once<W> (m, img, job, false, user_matches, job.capacity, !matches_on_device, total, &used, true, true);
+  if (rc != kFilterOverflow) {
+    job.d_matches = used;
+    return rc;
+  }
+  img->stats.fallback_count++;
+  img->stats.last_nb_candidates = 0;
+  ACMB200Match *out = user_matches;
+  if (!matches_on_device && job.capacity) {
+    if ((rc = img->d_matches.ensure (job.capacity * sizeof (ACMB200Match))))
+      return rc;
+    out = img->d_matches.as<ACMB200Match> ();
+  }
+  const uint64_t seg_lead = ((uint64_t)(m->max_depth ? m->max_depth - 1 : 0) + 15) / 16 * 16;
+  uint64_t produced = 0, grand = 0;
+  for (uint64_t start = 0; start < job.n; start += kDenseSegment) {
+    ScanJob sub = job;
+    const uint64_t lead = start ? seg_lead : 0, len = std::min<uint64_t> (kDenseSegment, job.n - start);
+    sub.d_text = reinterpret_cast<const unsigned char *> (job.d_text) + (start - lead) * W;
+    sub.n = len + lead;
+    sub.lead = start ? std::max<uint64_t> (lead, job.lead > start - lead ? job.lead - (start - lead) : 0) : job.lead;
+    sub.base = job.base + (start - lead);
+    sub.prefix_len = start ? 0 : job.prefix_len;
+    uint64_t seg_total = 0;
+    const uint64_t room = job.capacity > produced ? job.capacity - produced : 0;
+    rc = run_filter_once<W> (m, img, sub, true, out ? out + produced : nullptr, room, false, &seg_total, &used, start == 0, start + kDenseSegment >= job.n);
+    if (rc)
+      return rc;
+    produced += std::min<uint64_t> (seg_total, room);
+    grand += seg_total;
+  }
+  *total = grand;
+  job.d_matches = out;
+  return ACM_B200_OK;
 }
 
 /* ---- cursor bookkeeping (host, at most max_depth symbols) ------------------------------------------------------------ */

@@ -126,3 +126,30 @@ def test_config3_full_size_properties():
         parts.append(d_out[: k * 16].cpu().numpy().view(ac75().MATCH_DTYPE).copy())
     assert sum(len(p) for p in parts) == total and np.array_equal(np.concatenate(parts), recs)
     m.close(), o.close()
+
+
+def test_dense_fallback_runs_in_segments():
+    """A text whose candidate density is far above the filter's false-positive rate (4-letter alphabet: one position in five ends
+    with some keyword's last 4 symbols) overflows the sparse staging; the scan must fall back to the dense mode, which walks the
+    text in 64 Mi-symbol segments with left context, and still return exactly the oracle's records."""
+    rng = np.random.default_rng(21)
+    flat, offsets = random_patterns(60, lmin=7, lmax=11, seed=21, alphabet=4)
+    n = (64 << 20) + (3 << 20) + 12345  # crosses one segment boundary
+    text = rng.integers(0, 4, size=n).astype(np.uint8)
+    o = pyoracle.Oracle("port", 1)
+    o.insert_many(flat=flat, offsets=offsets)
+    want = o.scan(text, cap=1 << 24)
+    m = ac75().Machine(1)
+    m.insert_many(flat=flat, offsets=offsets)
+    m.set_option("engine", "filter")
+    got = m.scan(text, capacity=1 << 24)
+    st = m.stats()
+    assert st["engine"] == "filter" and st["fallback_count"] == 1
+    assert len(want) > 10_000 and np.array_equal(got, want), (len(got), len(want))
+    # with a lead and a base, as a shard would be scanned
+    lead = 5_000_000
+    got2 = m.scan(text, lead=lead, base=10**12, capacity=1 << 24)
+    w2 = want[want["end"] >= lead].copy()
+    w2["end"] += 10**12
+    assert np.array_equal(got2, w2)
+    m.close(), o.close()
