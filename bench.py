@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the scan path on B200 (text GB/s scanned + matches/s), next to the reference's CPU loop.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c4s] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c2|c4s|c5] [--impl ours|reference]
 
 A "step" is one pass of the hot path (acm_b200_scan_ex: every kernel of the engine) over this rank's shard of the
 synthetic text.  `value` is measured with the shard resident in HBM; `e2e` goes through the same C-ABI call with host
@@ -27,12 +27,34 @@ CONFIGS = {
     # name: (description, dictionary builder args, text kind, default GiB per GPU)
     "c3": dict(workload="BASELINE configs[2]: 100k random-byte patterns (len 4-32) over 8 GiB synthetic bytes, keywords planted every 4 KiB", nb_patterns=100_000, kind=0, gib=8.0),
     "c4s": dict(workload="BASELINE configs[3] single-GPU slice: 1M random-byte patterns (len 4-32) over 2 GiB synthetic bytes per GPU", nb_patterns=1_000_000, kind=0, gib=2.0),
+    "c5": dict(workload="BASELINE configs[4] slice: uint32 token ids, Zipf(1.0) over a 50k vocabulary, 200k n-gram keywords (len 2-8) cut from the stream, 64 Mi tokens per GPU",
+               nb_patterns=200_000, kind=5, gib=0.25, width=4),
     "c2": dict(workload="BASELINE configs[1]: 1k most frequent English words of the novel over 1 GiB synthetic printable ASCII, keywords planted every 4 KiB", nb_patterns=0, kind=1, gib=1.0),
 }
 TEXT_SEED, DICT_SEED, PLANT_SEED, PLANT_PERIOD = 0xC0FFEE, 0xD1C7, 0x5EED, 4096
 
 
+def zipf_tokens(n, first, vocab=50_000, seed=0xC0FFEE):
+    """Zipf(1.0) token ids by inverse CDF; block-seeded so that any rank can generate its own shard."""
+    cdf = np.cumsum(1.0 / np.arange(1, vocab + 1))
+    cdf /= cdf[-1]
+    out = np.empty(n, dtype=np.uint32)
+    blk = 1 << 22
+    for b0 in range(first // blk, (first + n + blk - 1) // blk):
+        r = np.random.default_rng([seed, b0]).random(blk)
+        toks = np.searchsorted(cdf, r).astype(np.uint32)
+        lo, hi = max(first, b0 * blk), min(first + n, (b0 + 1) * blk)
+        out[lo - first:hi - first] = toks[lo - b0 * blk:hi - b0 * blk]
+    return out
+
+
 def build_dictionary(cfg):
+    if cfg.get("width", 1) == 4:
+        stream = zipf_tokens(1 << 22, 0)
+        rng = np.random.default_rng(DICT_SEED)
+        starts, lens = rng.integers(0, len(stream) - 8, size=cfg["nb_patterns"]), rng.integers(2, 9, size=cfg["nb_patterns"])
+        flat = np.concatenate([stream[a:a + l] for a, l in zip(starts, lens)])
+        return flat, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
     if cfg["nb_patterns"]:
         rng = np.random.default_rng(DICT_SEED)
         lens = rng.integers(4, 33, size=cfg["nb_patterns"])
@@ -98,17 +120,23 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def reference_oracle(flat, offsets):
+def reference_oracle(flat, offsets, width=1):
     """The reference's own CPU implementation of the path (oracle/_ref, classic build: its Meyer build needs minutes to ingest 100k
     patterns), else the C restatement."""
     from oracle import pyoracle
 
     for kind, label in (("ref_classic", "reference"), ("ref_meyer", "reference"), ("port", "port")):
         if pyoracle.available(kind):
-            o = pyoracle.Oracle(kind, 1)
+            o = pyoracle.Oracle(kind, width)
             o.insert_many(flat=flat, offsets=offsets)
             return o, label, kind
     raise RuntimeError("no oracle library is built")
+
+
+def host_text(ac75, cfg, nb, first, flat, offsets):
+    if cfg.get("width", 1) == 4:
+        return zipf_tokens(nb, first)
+    return ac75.generate_text(nb, first=first, kind=cfg["kind"], seed=TEXT_SEED, plant_seed=PLANT_SEED, plant_period=PLANT_PERIOD, dict_flat=flat, dict_offsets=offsets)
 
 
 def run_reference(args, cfg, rank, world):
@@ -117,10 +145,11 @@ def run_reference(args, cfg, rank, world):
         return
     ac75 = entry.load_package()
     flat, offsets = build_dictionary(cfg)
-    oracle, label, kind = reference_oracle(flat, offsets)
+    width = cfg.get("width", 1)
+    oracle, label, kind = reference_oracle(flat, offsets, width)
     cores = host_cores()
-    sample = int(min(cores, 64) * (1 << 20) * (4 if cfg["nb_patterns"] == 0 else 1))
-    text = ac75.generate_text(sample, first=0, kind=cfg["kind"], seed=TEXT_SEED, plant_seed=PLANT_SEED, plant_period=PLANT_PERIOD, dict_flat=flat, dict_offsets=offsets)
+    sample = int(min(cores, 64) * (1 << 20) * (4 if cfg["nb_patterns"] == 0 else 1)) // width
+    text = host_text(ac75, cfg, sample, 0, flat, offsets)
     threads = min(cores, 64)
     for _ in range(max(args.warmup, 1)):  # also triggers the classic build's lazy fail-link construction
         oracle.scan_mt(text[: max(sample // 8, 1 << 16)], threads)
@@ -130,12 +159,12 @@ def run_reference(args, cfg, rank, world):
         secs.append(s)
         matches = m
     t = float(np.mean(secs))
-    gbs = sample / t / 1e9
+    gbs = sample * width / t / 1e9
     line = {"impl": "reference", "metric": "text_GB_per_s_scanned", "value": gbs, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "sample": f"first {sample >> 20} MiB of the same generated text per step"},
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if width == 1 else "u32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "sample": f"first {sample * width >> 20} MiB of the same generated text per step"},
             "matches_per_s": matches / t,
-            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": label, "sample": f"{kind}: acm_match+acm_get_match loop over the first {sample >> 20} MiB, {threads} threads (one cursor each)"},
+            "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": label, "sample": f"{kind}: acm_match+acm_get_match loop over the first {sample * width >> 20} MiB, {threads} threads (one cursor each)"},
             "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -174,10 +203,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     gib = args.gib if args.gib is not None else cfg["gib"]
-    shard = int(gib * (1 << 30)) // 4096 * 4096
+    width = cfg.get("width", 1)
+    shard = int(gib * (1 << 30)) // width // 4096 * 4096  # symbols per GPU
     flat, offsets = build_dictionary(cfg)
     t0 = time.time()
-    m = ac75.Machine(1)
+    m = ac75.Machine(width)
     m.insert_many(flat=flat, offsets=offsets)
     build_s = time.time() - t0
     if args.engine != "auto":
@@ -193,10 +223,13 @@ def main():
 
     stream = torch.cuda.Stream()  # the library launches every kernel of the scan on this stream; the events below are recorded on it
     torch.cuda.set_stream(stream)
-    d_text = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
-    ac75.generate_text(n, first=first, kind=cfg["kind"], seed=TEXT_SEED, plant_seed=PLANT_SEED, plant_period=PLANT_PERIOD, dict_flat=flat, dict_offsets=offsets,
-                       device_ptr=d_text.data_ptr(), stream=stream.cuda_stream)
-    cap = max(1 << 20, n // 512)
+    d_text = torch.empty(n * width + 64, dtype=torch.uint8, device="cuda")
+    if width == 4:
+        d_text[: n * 4].copy_(torch.from_numpy(zipf_tokens(n, first).view(np.uint8)))
+    else:
+        ac75.generate_text(n, first=first, kind=cfg["kind"], seed=TEXT_SEED, plant_seed=PLANT_SEED, plant_period=PLANT_PERIOD, dict_flat=flat, dict_offsets=offsets,
+                           device_ptr=d_text.data_ptr(), stream=stream.cuda_stream)
+    cap = max(1 << 20, n // 512) if width == 1 else max(1 << 20, 2 * n)
     d_matches = torch.empty(cap * 16, dtype=torch.uint8, device="cuda")
 
     def step_device():
@@ -241,14 +274,14 @@ def main():
         t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
-    total_bytes = shard * world  # symbols owned (the lead overlap is overhead, not counted)
+    total_bytes = shard * width * world  # bytes of the symbols owned (the lead overlap is overhead, not counted)
     value = total_bytes / (ms_step * 1e-3) / 1e9
 
     # end to end: host (pinned) text in, host (pinned) records out, through the same C-ABI call
     e2e = None
     if not args.no_e2e:
-        h_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-        h_text.copy_(d_text[:n])
+        h_text = torch.empty(n * width, dtype=torch.uint8, pin_memory=True)
+        h_text.copy_(d_text[: n * width])
         h_out = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
         torch.cuda.synchronize()
         e2e_steps = max(2, min(args.steps, 5))
@@ -265,7 +298,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         assert got == local_matches, (got, local_matches)
-        e2e = {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(min(got, cap) * 16 + 8),
+        e2e = {"value": total_bytes / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n * width), "d2h_bytes_per_step": int(min(got, cap) * 16 + 8),
                "ms_per_step": e2e_ms, "steps": e2e_steps}
         del h_text, h_out
 
@@ -276,7 +309,7 @@ def main():
 
     peak, peak_src = measured_peak()
     t_main = float(np.mean(main_ms)) * 1e-3
-    algo_bytes = n * 1 + local_matches * 16  # N*w + M*16 per launch of this rank
+    algo_bytes = n * width + local_matches * 16  # N*w + M*16 per launch of this rank
     achieved = algo_bytes / t_main / 1e9
     prof = {}
     try:
@@ -285,8 +318,8 @@ def main():
         pass
     line = {
         "metric": "text_GB_per_s_scanned", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "bytes_per_gpu": shard, "engine": st1["engine"], "nb_keywords": st1["nb_keywords"], "nb_states": st1["nb_states"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if width == 1 else "u32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "bytes_per_gpu": shard * width, "engine": st1["engine"], "nb_keywords": st1["nb_keywords"], "nb_states": st1["nb_states"],
                    "l2": "inputs larger than L2 (no flush needed)", "text_seed": hex(TEXT_SEED), "dict_seed": hex(DICT_SEED), "table_bytes": st1["table_bytes"],
                    "smem_bytes": st1["smem_bytes"], "dictionary_build_s": round(build_s, 2), "finalise_ms": round(st1["finalise_ms"], 1)},
         "matches_per_s": total_matches / (ms_step * 1e-3), "matches_per_step": total_matches, "candidates_per_step_rank0": cands,
@@ -299,16 +332,16 @@ def main():
         "gpu_launches": int(st1["total_kernel_launches"] - st0["total_kernel_launches"]),
     }
     if not args.no_cpu_baseline and world == 1:
-        oracle, label, kind = reference_oracle(flat, offsets)
-        sample = (2 << 20) if cfg["nb_patterns"] else (32 << 20)
-        text = ac75.generate_text(sample, first=0, kind=cfg["kind"], seed=TEXT_SEED, plant_seed=PLANT_SEED, plant_period=PLANT_PERIOD, dict_flat=flat, dict_offsets=offsets)
+        oracle, label, kind = reference_oracle(flat, offsets, width)
+        sample = ((2 << 20) if cfg["nb_patterns"] else (32 << 20)) // width
+        text = host_text(ac75, cfg, sample, 0, flat, offsets)
         oracle.count(text[: 1 << 16])  # classic build: lazy construction of the fail links outside the timed region
         oracle.reset_cursor()
         t0 = time.perf_counter()
         cm = oracle.count(text)
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": sample / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": label,
-                                "sample": f"{kind}: acm_match+acm_get_match loop over the first {sample >> 20} MiB of the same text, {cm} matches, {dt:.1f} s; host has {host_cores()} cores"}
+        line["cpu_baseline"] = {"value": sample * width / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": label,
+                                "sample": f"{kind}: acm_match+acm_get_match loop over the first {sample * width >> 20} MiB of the same text, {cm} matches, {dt:.1f} s; host has {host_cores()} cores"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
