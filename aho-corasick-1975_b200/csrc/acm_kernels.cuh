@@ -302,11 +302,11 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict
   uint32_t acc = 0; /* every test shifts its verdict in at bit 31 (one funnel shift); the first symbol ends at bit 32 - 16/W */
   auto push = [&] (uint32_t folded) {
     const unsigned long long p1 = (unsigned long long)folded * ACM_BLOOM_C1;
-    const uint32_t word = s_bloom[__umulhi ((uint32_t)p1, nwords)];
-    const uint32_t h1 = (uint32_t)(p1 >> 32), h2 = __umulhi (folded, ACM_BLOOM_C2);
-    uint32_t t = (word >> (h1 & 31u)) & (word >> (h2 & 31u));
+    const uint32_t lo = (uint32_t)p1, hi = (uint32_t)(p1 >> 32);
+    const uint32_t word = s_bloom[__umulhi (lo, nwords)];
+    uint32_t t = (word >> (hi & 31u)) & (word >> (lo & 31u));
     if (K > 2)
-      t &= word >> ((h2 >> 5) & 31u);
+      t &= word >> (__umulhi (folded, ACM_BLOOM_C2) & 31u);
     if (kTwoLevel) { /* survivors of the shared-memory level ask the L2-resident level */
       uint32_t word2 = 0;
       if (t & 1u)
@@ -324,7 +324,6 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict
       const uint32_t win = sh == 32 ? w[j] : __funnelshift_r (w[j - 1], w[j], sh);
       push (Q == 4 ? win : win >> (8 * (4 - Q)));
     }
-    return acc >> 16;
   } else if (W == 2) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -332,13 +331,12 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict
       const uint32_t pair = (i & 1) ? w[j] : __funnelshift_r (w[j - 1], w[j], 16); /* low half = s[i-1], high half = s[i] */
       push (Q == 2 ? pair : (pair >> 16));
     }
-    return acc >> 24;
   } else {
 #pragma unroll
     for (int i = 0; i < 4; i++)
       push (acm_fold_key (Q == 2 ? (((uint64_t)w[i + 1] << 32) | w[i]) : (uint64_t)w[i + 1]));
-    return acc >> 28;
   }
+  return acc >> (32 - 16 / W);
 }
 
 /* Membership of a 32-bit q-gram key in the compact set: normally one 16-byte load. */

@@ -34,7 +34,8 @@ acm_fold_key (uint64_t key) {
 /* Blocked Bloom filter in shared memory: one 32-bit word per key, k (2 or 3) bits inside it.
  *   p1 = folded * C1 (64-bit product): word index = mulhi (lo32 (p1), nwords)   (nwords need not be a power of two)
  *                                      bit a      = hi32 (p1) & 31              (bits 32..36 of the product: depend on every input bit)
- *   h2 = mulhi (folded, C2):           bit b      = h2 & 31,   bit c = (h2 >> 5) & 31
+ *                                      bit b      = lo32 (p1) & 31              (a bijection of the key's low 5 bits)
+ *   k = 3 only:                        bit c      = mulhi (folded, C2) & 31
  * The bit positions sit in the low 5 bits of a register on purpose: the GPU's funnel shift takes its amount modulo 32, so the
  * kernel needs no extraction instruction, and the multiplies run on the FMA pipe next to the ALU pipe that does the shifts. */
 ACM_HD uint32_t
@@ -51,10 +52,10 @@ acm_bloom_word (uint32_t folded, uint32_t nwords) {
 }
 ACM_HD uint32_t
 acm_bloom_mask (uint32_t folded, uint32_t k) {
-  const uint32_t h1 = acm_mulhi32 (folded, ACM_BLOOM_C1), h2 = acm_mulhi32 (folded, ACM_BLOOM_C2);
-  uint32_t m = (1u << (h1 & 31u)) | (1u << (h2 & 31u));
+  const uint32_t lo = folded * ACM_BLOOM_C1, hi = acm_mulhi32 (folded, ACM_BLOOM_C1);
+  uint32_t m = (1u << (hi & 31u)) | (1u << (lo & 31u));
   if (k > 2)
-    m |= 1u << ((h2 >> 5) & 31u);
+    m |= 1u << (acm_mulhi32 (folded, ACM_BLOOM_C2) & 31u);
   return m;
 }
 
