@@ -159,3 +159,22 @@ def test_capacity_is_reported():
     with pytest.raises(ac75().AcmError):
         m.scan(b"a" * 1000, capacity=10)
     m.close()
+
+
+def test_custom_comparator_machine_through_c_abi(tmp_path, novel):
+    """wchar_t letters + case-insensitive user comparator (the reference's own test setup): class-id remap + batch scan must equal
+    the per-symbol loop of the same machine, across insertions on a carried cursor.  Driven from C, as a user of the C-ABI would."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    libdir = os.path.join(ROOT, "aho-corasick-1975_b200")
+    exe = tmp_path / "custom_cmp_parity"
+    subprocess.run(["gcc", "-std=c11", "-O2", "-D_XOPEN_SOURCE=700", f"-I{os.path.join(ROOT, 'include')}", "-o", str(exe), os.path.join(ROOT, "tests", "csrc", "custom_cmp_parity.c"),
+                    f"-L{libdir}", "-lac75", f"-Wl,-rpath,{libdir}"], check=True)
+    txt = tmp_path / "novel.txt"
+    txt.write_bytes(bytes(b if b < 128 else 32 for b in novel))
+    r = subprocess.run([str(exe), str(txt)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("records identical") == 4 and "width 4" in r.stdout
