@@ -327,10 +327,13 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
 
   auto count_k = dfa_scan_kernel<Entry, kShared, false>;
-  auto emit_k = dfa_scan_kernel<Entry, kShared, true>;
+  /* pass 2: warp-cooperative emit when positions relative to a warp's 32 chunks fit 32 bits (always, short of absurd chunk sizes) */
+  const bool coop = p.chunk * 32 < (1ull << 32);
+  auto emit_k = coop ? dfa_emit_kernel<Entry, kShared> : dfa_scan_kernel<Entry, kShared, true>;
+  const size_t emit_smem = smem + (coop ? sizeof (EmitWarpState) * (threads / 32) : 0);
   CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  img->stats.smem_bytes = smem;
+  CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+  img->stats.smem_bytes = emit_smem;
 
   CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
   count_k<<<grid, threads, smem, job.st>>> (p);
@@ -355,7 +358,7 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
       p.matches = img->d_matches.as<ACMB200Match> ();
     }
     p.capacity = want;
-    emit_k<<<grid, threads, smem, job.st>>> (p);
+    emit_k<<<grid, threads, emit_smem, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
     img->stats.main_kernel_launches += 1;
     img->stats.total_kernel_launches += 1;

@@ -510,7 +510,7 @@ acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_bud
   else if (!strcmp (m->engine_override, "filter"))
     engine = ACM_B200_ENGINE_FILTER;
   const uint64_t smem_table = (uint64_t)n * K * 2;
-  const int smem_ok = t->width == 1 && n <= 0xFFFF && smem_table + 1024 <= smem_budget;
+  const int smem_ok = t->width == 1 && n <= 0xFFFF && smem_table + 1024 + 32 * 896 <= smem_budget; /* + the emit pass's per-warp queues */
   const int global_ok = t->width == 1 && (uint64_t)n * K * 4 <= (8ull << 30);
   if (engine == ACM_B200_ENGINE_DFA_SMEM && !smem_ok)
     engine = ACM_B200_ENGINE_AUTO;

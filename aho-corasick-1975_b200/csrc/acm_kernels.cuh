@@ -140,7 +140,7 @@ struct DfaParams {
 };
 
 template <typename Entry, bool kShared, bool kEmit>
-__global__ void __launch_bounds__ (kShared ? 1024 : 256)
+__global__ void __launch_bounds__ (kShared ? 1024 : 256, kShared ? 1 : 2)
 dfa_scan_kernel (const __grid_constant__ DfaParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
   uint8_t *s_class = smem;
@@ -197,6 +197,150 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
       step (p.text[pos], pos);
     if (!kEmit)
       p.chunk_counts[c] = count;
+  }
+}
+
+/* Pass 2 of the DFA engines, warp-cooperative.  The 32 lanes of a warp walk 32 neighbouring chunks in lockstep.  Whenever a lane
+ * reaches a state with outputs it appends an event (lane, position, state) to the warp's queue in shared memory (ballot/popc
+ * compaction); as soon as 32 events are queued, ALL lanes expand one event each into its records.  The output cursor of every
+ * chunk lives in shared memory; events of the same chunk inside one batch are ordered with match_any, so each chunk's records
+ * stay in position order and the whole output stays in the reference's emission order. */
+constexpr int kEmitQueue = 64; /* events per warp */
+struct EmitWarpState {
+  unsigned long long cursor[32]; /* next record index of each lane's chunk */
+  uint2 queue[kEmitQueue];       /* x = position relative to the warp's first chunk, y = lane << 27 | state */
+  uint32_t batch_records[32];    /* records of each event of the batch being expanded */
+};
+
+template <typename Entry, bool kShared>
+__global__ void __launch_bounds__ (kShared ? 1024 : 256, kShared ? 1 : 2)
+dfa_emit_kernel (const __grid_constant__ DfaParams p) {
+  extern __shared__ __align__ (16) unsigned char smem[];
+  uint8_t *s_class = smem;
+  EmitWarpState *s_emit = reinterpret_cast<EmitWarpState *> (smem + 256);
+  Entry *s_delta = reinterpret_cast<Entry *> (smem + 256 + sizeof (EmitWarpState) * (blockDim.x >> 5));
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_class[i] = p.class_of_byte[i];
+  if (kShared) {
+    const uint4 *src = reinterpret_cast<const uint4 *> (p.delta);
+    uint4 *dst = reinterpret_cast<uint4 *> (s_delta);
+    const uint32_t vecs = (uint32_t)(((uint64_t)p.nb_states * p.K * sizeof (Entry) + 15) / 16);
+    for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads ();
+  const Entry *__restrict__ delta = kShared ? s_delta : reinterpret_cast<const Entry *> (p.delta);
+  const uint32_t K = p.K, thr = p.out_threshold;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  EmitWarpState &ws = s_emit[threadIdx.x >> 5];
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+
+  for (uint64_t c0 = warp_global * 32; c0 < p.nchunks; c0 += nwarps * 32) {
+    const uint64_t c = c0 + lane;
+    const bool have = c < p.nchunks;
+    const uint64_t warp_origin = c0 * p.chunk;
+    const uint64_t start = have ? c * p.chunk : p.n;
+    const uint64_t end = have ? min (p.n, start + p.chunk) : p.n;
+    const uint64_t report_from = max (start, p.lead);
+    const bool from_origin = start <= p.warm;
+    uint32_t state = from_origin ? p.init_state : 0;
+    uint64_t pos = !have ? p.n : (from_origin ? 0 : (start - p.warm) & ~(uint64_t)15);
+    ws.cursor[lane] = have ? p.chunk_offsets[c] : 0;
+    uint32_t queued = 0; /* warp-uniform */
+    __syncwarp ();
+
+    /* expands up to 32 queued events, one per lane */
+    auto drain = [&] (uint32_t count) {
+      const bool mine = (uint32_t)lane < count;
+      uint32_t L = 32u + lane, lo = 0, n = 0;
+      uint64_t at_pos = 0;
+      if (mine) {
+        const uint2 ev = ws.queue[lane];
+        L = ev.y >> 27;
+        const uint32_t o = (ev.y & 0x07FFFFFFu) - thr;
+        lo = p.out_offsets[o];
+        n = p.out_offsets[o + 1] - lo;
+        at_pos = warp_origin + ev.x;
+      }
+      /* events of the same chunk in this batch: earlier ones (lower queue index) come first */
+      ws.batch_records[lane] = n;
+      const uint32_t same = __match_any_sync (kFull, L);
+      const bool last_of_chunk = mine && (same >> lane) == 1u;
+      __syncwarp ();
+      uint32_t before = 0;
+      for (uint32_t earlier = same & lanes_below; earlier; earlier &= earlier - 1)
+        before += ws.batch_records[__ffs (earlier) - 1];
+      unsigned long long out = mine ? ws.cursor[L] + before : 0;
+      __syncwarp ();
+      if (last_of_chunk)
+        ws.cursor[L] = out + n;
+      for (uint32_t j = 0; j < n; j++, out++)
+        if (out < p.capacity) {
+          const acm_output e = p.out_entries[lo + j];
+          p.matches[out] = ACMB200Match{ p.base + at_pos, e.keyword, e.length };
+        }
+      __syncwarp ();
+      /* shift the rest of the queue to the front */
+      const uint32_t rest = queued - count;
+      uint2 moved = make_uint2 (0, 0);
+      if ((uint32_t)lane < rest)
+        moved = ws.queue[count + lane];
+      __syncwarp ();
+      if ((uint32_t)lane < rest)
+        ws.queue[lane] = moved;
+      queued = rest;
+      __syncwarp ();
+    };
+
+    while (__any_sync (kFull, pos < end)) {
+      /* next 16 bytes of this lane's walk (fewer at the end of its chunk) */
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, nvalid = 0;
+      if (pos + 16 <= end) {
+        const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
+        w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        nvalid = 16;
+      } else if (pos < end) {
+        nvalid = (uint32_t)(end - pos);
+#pragma unroll
+        for (int i = 0; i < 16; i++) { /* compile-time i: the words stay in registers */
+          const uint32_t b = (uint32_t)i < nvalid ? (uint32_t)p.text[pos + i] << (8 * (i & 3)) : 0u;
+          if ((i >> 2) == 0)
+            w0 |= b;
+          else if ((i >> 2) == 1)
+            w1 |= b;
+          else if ((i >> 2) == 2)
+            w2 |= b;
+          else
+            w3 |= b;
+        }
+      }
+      /* bytes before `first_reported` belong to the warm-up (or the caller's lead): walked, never reported */
+      const uint32_t first_reported = report_from > pos ? (uint32_t)min ((uint64_t)16, report_from - pos) : 0u;
+      const uint32_t rel0 = (uint32_t)(pos - warp_origin), tag = (uint32_t)lane << 27;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t word = (i >> 2) == 0 ? w0 : ((i >> 2) == 1 ? w1 : ((i >> 2) == 2 ? w2 : w3));
+        bool event = false;
+        if ((uint32_t)i < nvalid) {
+          state = delta[state * K + s_class[(word >> (8 * (i & 3))) & 0xFFu]];
+          event = state >= thr && (uint32_t)i >= first_reported;
+        }
+        const uint32_t evmask = __ballot_sync (kFull, event);
+        if (evmask) {
+          if (event)
+            ws.queue[queued + __popc (evmask & lanes_below)] = make_uint2 (rel0 + i, tag | state);
+          queued += __popc (evmask);
+          __syncwarp ();
+          if (queued >= 32)
+            drain (32);
+        }
+      }
+      pos += nvalid;
+    }
+    if (queued)
+      drain (queued);
+    __syncwarp ();
   }
 }
 
