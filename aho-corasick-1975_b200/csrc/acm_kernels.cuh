@@ -212,6 +212,53 @@ struct EmitWarpState {
   uint32_t batch_records[32];    /* records of each event of the batch being expanded */
 };
 
+/* Expands the first `count` (<= 32) queued events of a warp, one per lane, into records; returns the new queue length. */
+__device__ __noinline__ uint32_t
+emit_drain (EmitWarpState &ws, const DfaParams &p, uint32_t thr, uint64_t warp_origin, uint32_t queued, uint32_t count) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+
+      const bool mine = (uint32_t)lane < count;
+      uint32_t L = 32u + lane, lo = 0, n = 0;
+      uint64_t at_pos = 0;
+      if (mine) {
+        const uint2 ev = ws.queue[lane];
+        L = ev.y >> 27;
+        const uint32_t o = (ev.y & 0x07FFFFFFu) - thr;
+        lo = p.out_offsets[o];
+        n = p.out_offsets[o + 1] - lo;
+        at_pos = warp_origin + ev.x;
+      }
+      /* events of the same chunk in this batch: earlier ones (lower queue index) come first */
+      ws.batch_records[lane] = n;
+      const uint32_t same = __match_any_sync (kFull, L);
+      const bool last_of_chunk = mine && (same >> lane) == 1u;
+      __syncwarp ();
+      uint32_t before = 0;
+      for (uint32_t earlier = same & lanes_below; earlier; earlier &= earlier - 1)
+        before += ws.batch_records[__ffs (earlier) - 1];
+      unsigned long long out = mine ? ws.cursor[L] + before : 0;
+      __syncwarp ();
+      if (last_of_chunk)
+        ws.cursor[L] = out + n;
+      for (uint32_t j = 0; j < n; j++, out++)
+        if (out < p.capacity) {
+          const acm_output e = p.out_entries[lo + j];
+          p.matches[out] = ACMB200Match{ p.base + at_pos, e.keyword, e.length };
+        }
+      __syncwarp ();
+      /* shift the rest of the queue to the front */
+      const uint32_t rest = queued - count;
+      uint2 moved = make_uint2 (0, 0);
+      if ((uint32_t)lane < rest)
+        moved = ws.queue[count + lane];
+      __syncwarp ();
+      if ((uint32_t)lane < rest)
+        ws.queue[lane] = moved;
+      __syncwarp ();
+      return rest;
+    }
+
 template <typename Entry, bool kShared>
 __global__ void __launch_bounds__ (kShared ? 1024 : 256, kShared ? 1 : 2)
 dfa_emit_kernel (const __grid_constant__ DfaParams p) {
@@ -250,48 +297,7 @@ dfa_emit_kernel (const __grid_constant__ DfaParams p) {
     uint32_t queued = 0; /* warp-uniform */
     __syncwarp ();
 
-    /* expands up to 32 queued events, one per lane */
-    auto drain = [&] (uint32_t count) {
-      const bool mine = (uint32_t)lane < count;
-      uint32_t L = 32u + lane, lo = 0, n = 0;
-      uint64_t at_pos = 0;
-      if (mine) {
-        const uint2 ev = ws.queue[lane];
-        L = ev.y >> 27;
-        const uint32_t o = (ev.y & 0x07FFFFFFu) - thr;
-        lo = p.out_offsets[o];
-        n = p.out_offsets[o + 1] - lo;
-        at_pos = warp_origin + ev.x;
-      }
-      /* events of the same chunk in this batch: earlier ones (lower queue index) come first */
-      ws.batch_records[lane] = n;
-      const uint32_t same = __match_any_sync (kFull, L);
-      const bool last_of_chunk = mine && (same >> lane) == 1u;
-      __syncwarp ();
-      uint32_t before = 0;
-      for (uint32_t earlier = same & lanes_below; earlier; earlier &= earlier - 1)
-        before += ws.batch_records[__ffs (earlier) - 1];
-      unsigned long long out = mine ? ws.cursor[L] + before : 0;
-      __syncwarp ();
-      if (last_of_chunk)
-        ws.cursor[L] = out + n;
-      for (uint32_t j = 0; j < n; j++, out++)
-        if (out < p.capacity) {
-          const acm_output e = p.out_entries[lo + j];
-          p.matches[out] = ACMB200Match{ p.base + at_pos, e.keyword, e.length };
-        }
-      __syncwarp ();
-      /* shift the rest of the queue to the front */
-      const uint32_t rest = queued - count;
-      uint2 moved = make_uint2 (0, 0);
-      if ((uint32_t)lane < rest)
-        moved = ws.queue[count + lane];
-      __syncwarp ();
-      if ((uint32_t)lane < rest)
-        ws.queue[lane] = moved;
-      queued = rest;
-      __syncwarp ();
-    };
+    auto drain = [&] (uint32_t count) { queued = emit_drain (ws, p, thr, warp_origin, queued, count); };
 
     while (__any_sync (kFull, pos < end)) {
       /* next 16 bytes of this lane's walk (fewer at the end of its chunk) */
@@ -318,22 +324,37 @@ dfa_emit_kernel (const __grid_constant__ DfaParams p) {
       /* bytes before `first_reported` belong to the warm-up (or the caller's lead): walked, never reported */
       const uint32_t first_reported = report_from > pos ? (uint32_t)min ((uint64_t)16, report_from - pos) : 0u;
       const uint32_t rel0 = (uint32_t)(pos - warp_origin), tag = (uint32_t)lane << 27;
+      auto enqueue = [&] (uint32_t evmask, bool event, int i) {
+        if (event)
+          ws.queue[queued + __popc (evmask & lanes_below)] = make_uint2 (rel0 + i, tag | state);
+        queued += __popc (evmask);
+        __syncwarp ();
+        if (queued >= 32)
+          drain (32);
+      };
+      if (__all_sync (kFull, nvalid == 16 && first_reported == 0)) {
+        /* usual case, warp-uniform: every lane has 16 reportable bytes -- no per-byte validity logic */
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const uint32_t word = (i >> 2) == 0 ? w0 : ((i >> 2) == 1 ? w1 : ((i >> 2) == 2 ? w2 : w3));
-        bool event = false;
-        if ((uint32_t)i < nvalid) {
+        for (int i = 0; i < 16; i++) {
+          const uint32_t word = (i >> 2) == 0 ? w0 : ((i >> 2) == 1 ? w1 : ((i >> 2) == 2 ? w2 : w3));
           state = delta[state * K + s_class[(word >> (8 * (i & 3))) & 0xFFu]];
-          event = state >= thr && (uint32_t)i >= first_reported;
+          const bool event = state >= thr;
+          const uint32_t evmask = __ballot_sync (kFull, event);
+          if (evmask)
+            enqueue (evmask, event, i);
         }
-        const uint32_t evmask = __ballot_sync (kFull, event);
-        if (evmask) {
-          if (event)
-            ws.queue[queued + __popc (evmask & lanes_below)] = make_uint2 (rel0 + i, tag | state);
-          queued += __popc (evmask);
-          __syncwarp ();
-          if (queued >= 32)
-            drain (32);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const uint32_t word = (i >> 2) == 0 ? w0 : ((i >> 2) == 1 ? w1 : ((i >> 2) == 2 ? w2 : w3));
+          bool event = false;
+          if ((uint32_t)i < nvalid) {
+            state = delta[state * K + s_class[(word >> (8 * (i & 3))) & 0xFFu]];
+            event = state >= thr && (uint32_t)i >= first_reported;
+          }
+          const uint32_t evmask = __ballot_sync (kFull, event);
+          if (evmask)
+            enqueue (evmask, event, i);
         }
       }
       pos += nvalid;
