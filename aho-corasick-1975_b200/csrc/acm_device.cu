@@ -308,10 +308,15 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   p.out_threshold = t.out_threshold;
   p.out_offsets = img->d_out_offsets.as<uint32_t> ();
   p.out_entries = img->d_out_entries.as<acm_output> ();
+  p.nb_out_states = t.nb_dfa_states - t.out_threshold;
   memcpy (p.class_of_byte, t.class_of_byte, 256);
 
   const int threads = kShared ? 1024 : 256;
-  const size_t smem = 256 + (kShared ? ((size_t)t.nb_dfa_states * t.nb_classes * sizeof (Entry) + 15) / 16 * 16 : 0);
+  size_t smem = 256 + (kShared ? ((size_t)t.nb_dfa_states * t.nb_classes * sizeof (Entry) + 15) / 16 * 16 : 0);
+  /* pass 1: a uint16 records-per-state table after the delta table when it fits and no state has more than 65535 records */
+  const size_t counts_bytes = ((size_t)p.nb_out_states * 2 + 15) / 16 * 16;
+  p.counts_in_smem = t.max_out_records <= 0xFFFF && smem + counts_bytes + 1024 <= img->smem_optin && counts_bytes <= 32768;
+  const size_t count_smem = smem + (p.counts_in_smem ? counts_bytes : 0);
   const int blocks_per_sm = kShared ? 1 : 8;
   uint64_t want_threads = m->option_threads ? m->option_threads : (uint64_t)img->sm_count * blocks_per_sm * threads;
   const uint64_t min_chunk = std::max<uint64_t> (256, (uint64_t)(4 * p.warm + 15) / 16 * 16);
@@ -331,12 +336,12 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   const bool coop = p.chunk * 32 < (1ull << 32);
   auto emit_k = coop ? dfa_emit_kernel<Entry, kShared> : dfa_scan_kernel<Entry, kShared, true>;
   const size_t emit_smem = smem + (coop ? sizeof (EmitWarpState) * (threads / 32) : 0);
-  CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)count_smem));
   CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
   img->stats.smem_bytes = emit_smem;
 
   CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
-  count_k<<<grid, threads, smem, job.st>>> (p);
+  count_k<<<grid, threads, count_smem, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
   CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
   if ((rc = device_exclusive_scan (img, p.chunk_counts, p.nchunks, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))

@@ -231,6 +231,8 @@ build_dfa (struct _ac_machine *m, struct acm_tables *t, struct _ac_state **by_de
   for (uint32_t i = 0; i < nout; i++) {
     t->out_offsets[i] = (uint32_t)total;
     total += of_dfa[i]->nb_outputs;
+    if (of_dfa[i]->nb_outputs > t->max_out_records)
+      t->max_out_records = of_dfa[i]->nb_outputs > 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)of_dfa[i]->nb_outputs;
   }
   if (total > 0xFFFFFFFFull) {
     free (of_dfa);

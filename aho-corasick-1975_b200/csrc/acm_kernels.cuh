@@ -132,6 +132,8 @@ struct DfaParams {
   uint32_t K, nb_states, out_threshold;
   const uint32_t *out_offsets;
   const acm_output *out_entries;
+  uint32_t nb_out_states;        /* states >= out_threshold */
+  uint32_t counts_in_smem;       /* pass 1 keeps a uint16 records-per-state table in shared memory (small dictionaries) */
   uint32_t *chunk_counts;        /* pass 1 out */
   const uint64_t *chunk_offsets; /* pass 2 in */
   ACMB200Match *matches;
@@ -155,9 +157,15 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     for (uint32_t i = threadIdx.x; i < vecs; i += blockDim.x)
       dst[i] = src[i];
   }
+  /* records per output state, next to the table, when the host found room for it (pass 1 only needs the count) */
+  uint16_t *s_counts = reinterpret_cast<uint16_t *> (smem + 256 + (kShared ? ((size_t)p.nb_states * p.K * sizeof (Entry) + 15) / 16 * 16 : 0));
+  if (!kEmit && p.counts_in_smem)
+    for (uint32_t i = threadIdx.x; i < p.nb_out_states; i += blockDim.x)
+      s_counts[i] = (uint16_t)(p.out_offsets[i + 1] - p.out_offsets[i]);
   __syncthreads ();
   const Entry *__restrict__ delta = kShared ? s_delta : reinterpret_cast<const Entry *> (p.delta);
   const uint32_t K = p.K, thr = p.out_threshold;
+  const bool smem_counts = !kEmit && p.counts_in_smem;
 
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t start = c * p.chunk;
@@ -173,7 +181,12 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     auto step = [&] (uint32_t byte, uint64_t at) {
       state = delta[state * K + s_class[byte]];
       if (state >= thr && at >= report_from) {
-        const uint32_t o = state - thr, lo = p.out_offsets[o], hi = p.out_offsets[o + 1];
+        const uint32_t o = state - thr;
+        if (smem_counts) {
+          count += s_counts[o];
+          return;
+        }
+        const uint32_t lo = p.out_offsets[o], hi = p.out_offsets[o + 1];
         if (kEmit) {
           for (uint32_t j = lo; j < hi; j++, out++)
             if (out < p.capacity) {

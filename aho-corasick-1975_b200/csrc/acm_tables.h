@@ -116,6 +116,7 @@ struct acm_tables {
   uint32_t *out_offsets;      /* [nb_dfa_states - out_threshold + 1] */
   acm_output *out_entries;    /* longest first */
   uint64_t nb_out_entries;
+  uint32_t max_out_records;   /* largest output set */
   uint32_t *dfa_of_state;     /* host state id -> dfa state (to start from a carried cursor) */
   /* --- filter engine --- */
   uint32_t q;                 /* symbols per filter window = min(lmin, 4 for bytes / 2 otherwise) */
