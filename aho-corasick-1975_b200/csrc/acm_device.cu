@@ -383,7 +383,6 @@ static int
 run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool dense, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily, uint64_t *total,
                  ACMB200Match **out_used, bool first_segment, bool last_segment) {
   const acm_tables &t = img->tab;
-  constexpr int kPasses = 1;
   const int kRowsOpt = m->option_tile_rows == 2 ? 2 : 4; /* rows of 512 bytes per warp tile (tuning knob) */
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
   {
@@ -393,8 +392,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.lead = job.lead;
     p.base = job.base;
     p.q = t.q;
-    p.tile_rows = kRowsOpt;
-    p.tile_syms = kRowsOpt * kPasses * 512 / W;
+    p.tile_syms = kRowsOpt * 512 / W;
     p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
     p.bloom = img->d_bloom.as<uint32_t> ();
     p.bloom_words = t.bloom_words;
@@ -443,8 +441,8 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
     const int K = t.bloom_k > 2 ? 3 : 2;
 #define ACM_F1_(Q_, K_, R_)                                                                                                                      \
-  (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, kPasses, Q_, K_, true, true> : filter_scan_kernel<W, R_, kPasses, Q_, K_, false, true>)       \
-            : (ordered ? filter_scan_kernel<W, R_, kPasses, Q_, K_, true, false> : filter_scan_kernel<W, R_, kPasses, Q_, K_, false, false>))
+  (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, true> : filter_scan_kernel<W, R_, Q_, K_, false, true>)       \
+            : (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, false> : filter_scan_kernel<W, R_, Q_, K_, false, false>))
 #define ACM_F1(Q_, K_)                                                                                                                           \
   if (p.q == Q_ && K == K_)                                                                                                                      \
     f1 = kRowsOpt == 2 ? ACM_F1_ (Q_, K_, 2) : ACM_F1_ (Q_, K_, 4)

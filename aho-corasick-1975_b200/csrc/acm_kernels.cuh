@@ -385,7 +385,6 @@ struct FilterParams {
   const void *text;
   uint64_t n, lead, base;
   uint32_t q;
-  uint32_t tile_rows;  /* 512-byte rows per warp tile */
   uint32_t tile_syms;  /* symbols per tile */
   uint64_t ntiles;
   const uint32_t *bloom;
@@ -536,7 +535,7 @@ qset_contains (const FilterParams &p, uint32_t key) {
  * kOrdered: raw hits are staged in position order with a warp scan (used by the dense fallback, where a tile may hold thousands
  * of candidates); otherwise they are staged through a shared-memory counter in any order and the few survivors of the exact
  * confirmation are sorted afterwards -- fewer instructions when hits are rare. */
-template <int W, int kRows, int kPasses, int Q, int K, bool kOrdered, bool kTwoLevel>
+template <int W, int kRows, int Q, int K, bool kOrdered, bool kTwoLevel>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -553,14 +552,12 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   uint16_t *stage = reinterpret_cast<uint16_t *> (stage_count + 4);
   constexpr int kSyms = 16 / W;        /* symbols per lane per row */
   constexpr int kRowSyms = 32 * kSyms; /* symbols per row */
-  constexpr uint32_t kPassSyms = kRows * kRowSyms;    /* symbols filtered per pass (kRows loads in flight per lane) */
-  constexpr uint32_t kTileSyms = kPasses * kPassSyms; /* a tile = kPasses passes sharing one staging / confirmation / reservation */
+  constexpr uint32_t kTileSyms = kRows * kRowSyms; /* symbols per tile: kRows loads in flight per lane */
   constexpr uint32_t q = Q;
   const uint32_t nwords = p.bloom_words, stage_cap = p.stage_cap;
   const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
   const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
 
-  static_assert (kPasses == 1, "a tile is one pass of kRows rows");
   /* The rows of a tile live in registers; the loads of the NEXT tile are issued right after the current tile has been filtered
    * and staged (its rows are dead by then), so their latency hides behind the confirmation step instead of stalling the filter. */
   uint4 v[kRows];
@@ -624,9 +621,6 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       __syncwarp ();
     }
 
-    {
-    constexpr int pass = 0;
-    const uint64_t pass_base = tile_base;
     uint32_t hits[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
@@ -638,7 +632,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
     if (!interior) { /* drop positions outside [first_valid, n) */
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
-        const uint64_t pos0 = pass_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
+        const uint64_t pos0 = tile_base + (uint64_t)r * kRowSyms + (uint64_t)lane * kSyms;
         uint32_t keep = 0;
         for (int i = 0; i < kSyms; i++)
           if (pos0 + i >= first_valid && pos0 + i < p.n)
@@ -670,7 +664,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         const uint32_t total = __shfl_sync (kFull, mine, 31);
         uint32_t at = row_start + mine - __popc (hits[r]);
         uint32_t h = hits[r];
-        const uint32_t rel0 = (uint32_t)(pass * kPassSyms + r * kRowSyms + lane * kSyms);
+        const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
         while (h) {
           const int i = __ffs (h) - 1;
           h &= h - 1;
@@ -693,7 +687,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
           uint32_t h = hits[r];
-          const uint32_t rel0 = (uint32_t)(pass * kPassSyms + r * kRowSyms + lane * kSyms);
+          const uint32_t rel0 = (uint32_t)(r * kRowSyms + lane * kSyms);
           while (h) {
             const int i = __ffs (h) - 1;
             h &= h - 1;
@@ -704,7 +698,6 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         }
       }
     }
-    } /* filter + staging */
     if (tile + tile_stride < p.ntiles)
       load_tile (tile + tile_stride); /* in flight during the confirmation below */
     if (!kOrdered) {
