@@ -97,20 +97,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Samples that arrived inside [t_begin, t_end] (the timed region); if fewer than 3, every sample taken under load
+        (warm-up + timed region), flagged in `window`."""
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if t_begin is not None and t_begin <= t <= t_end + 0.05]
+        window = "timed region"
+        rows = inside
+        if len(rows) < 3:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than the sampler's period)"
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        self.window = window
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def host_cores():
@@ -249,14 +257,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        local_matches = step_device()
-        exchange(local_matches)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)  # nvidia-smi needs a moment before its first sample
+    t_load = time.time()
+    while True:  # warm-up: at least W steps, and long enough for the clock sampler to see the GPU under load
+        for _ in range(max(args.warmup, 1)):
+            local_matches = step_device()
+            exchange(local_matches)
+        if args.warmup == 0 or time.time() - t_load > 0.25:
+            break
     assert args.warmup == 0 or local_matches <= cap, f"record buffer too small: {local_matches} > {cap}"
     st0 = m.stats()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_begin = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     main_ms, kernel_ms, cands = [], [], 0
     ev0.record(stream)
@@ -269,7 +283,7 @@ def main():
         cands = s["last_nb_candidates"]
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.time())
     st1 = m.stats()
     ms_step = ev0.elapsed_time(ev1) / max(args.steps, 1)
     if world > 1:
