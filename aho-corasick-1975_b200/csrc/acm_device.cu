@@ -85,11 +85,11 @@ struct acm_device_image {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
   DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
-  DevBuf d_text, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
+  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
@@ -106,14 +106,19 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_text2, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
     if (e)
       cudaEventDestroy (e);
+  for (cudaEvent_t e : img->ev_copy)
+    if (e)
+      cudaEventDestroy (e);
   if (img->stream)
     cudaStreamDestroy (img->stream);
+  if (img->copy_stream)
+    cudaStreamDestroy (img->copy_stream);
   if (img->h_small)
     cudaFreeHost (img->h_small);
   acm_free_tables (&img->tab);
@@ -154,7 +159,10 @@ finalise_locked (ACMachine *m, int device) {
     CUDA_TRY (cudaDeviceGetAttribute (&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     img->smem_optin = (size_t)v;
     CUDA_TRY (cudaStreamCreateWithFlags (&img->stream, cudaStreamNonBlocking));
+    CUDA_TRY (cudaStreamCreateWithFlags (&img->copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t &e : img->ev)
+      CUDA_TRY (cudaEventCreate (&e));
+    for (cudaEvent_t &e : img->ev_copy)
       CUDA_TRY (cudaEventCreate (&e));
     CUDA_TRY (cudaMallocHost (&img->h_small, sizeof (*img->h_small)));
     int rc = img->d_small.ensure (sizeof (*img->h_small));
@@ -247,6 +255,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_bloom_k = strtoull (value, 0, 10), m->generation++;
   else if (!strcmp (key, "threads"))
     m->option_threads = strtoull (value, 0, 10);
+  else if (!strcmp (key, "stream_bytes"))
+    m->option_stream_bytes = strtoull (value, 0, 10);
   else
     rc = ACM_B200_ERR_INVALID;
   acm_unlock (m);
@@ -625,14 +635,50 @@ acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
       return finish (fail (ACM_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString (e_)));    \
   } while (0)
 
-  if (scan->nb_symbols) {
+  auto run_engine = [&] (ScanJob &job, uint64_t *tot, bool out_on_device, ACMB200Match *out) -> int {
+    switch (t.engine) {
+      case ACM_B200_ENGINE_DFA_SMEM:
+        return run_dfa<uint16_t, true> (m, img, job, tot, out_on_device, out);
+      case ACM_B200_ENGINE_DFA_GLOBAL:
+        return run_dfa<uint32_t, false> (m, img, job, tot, out_on_device, out);
+      default:
+        return w == 1 ? run_filter<1> (m, img, job, tot, out_on_device, out)
+                      : (w == 2 ? run_filter<2> (m, img, job, tot, out_on_device, out) : run_filter<4> (m, img, job, tot, out_on_device, out));
+    }
+  };
+  /* kernel times of the run that just finished (its events are recorded on st, already synchronised) */
+  auto add_kernel_times = [&] () {
+    float ms = 0, a = 0, b = 0;
+    cudaEventElapsedTime (&ms, img->ev[0], img->ev[3]);
+    stats.scan_kernel_ms += ms;
+    cudaEventElapsedTime (&a, img->ev[0], img->ev[1]);
+    if (t.engine != ACM_B200_ENGINE_FILTER)
+      cudaEventElapsedTime (&b, img->ev[2], img->ev[3]);
+    stats.main_kernel_ms += a + b;
+  };
+  /* carried cursor: DFA engines start chunk 0 from its state, the filter engine sees its string as a virtual prefix */
+  auto apply_cursor = [&] (ScanJob &job) -> int {
+    if (t.engine == ACM_B200_ENGINE_FILTER) {
+      if (from->depth > 1024)
+        return fail (ACM_B200_ERR_INVALID, "cursor deeper than 1024 symbols%s", "");
+      job.prefix_len = from->depth;
+      uint32_t k = from->depth;
+      for (const ACState *s = from; s->parent; s = s->parent)
+        img->h_small->prefix[--k] = acm_symbol_of_state (m, s);
+    } else
+      job.init_dfa_state = t.dfa_of_state[from->id];
+    return ACM_B200_OK;
+  };
+  const uint64_t stream_bytes = m->option_stream_bytes ? m->option_stream_bytes : (256ull << 20);
+
+  if (scan->nb_symbols && (scan->text_on_device || scan->nb_symbols * w <= stream_bytes)) {
+    /* ---- one run over the whole text ---- */
     ScanJob job = {};
     job.n = scan->nb_symbols;
     job.lead = scan->lead;
     job.base = scan->base;
     job.capacity = scan->capacity;
     job.st = st;
-    /* text */
     if (scan->text_on_device) {
       if ((uintptr_t)scan->text & 15)
         return finish (fail (ACM_B200_ERR_INVALID, "device text must be 16-byte aligned%s", ""));
@@ -645,61 +691,82 @@ acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
       TRY_LOCKED (cudaEventRecord (img->ev[5], st));
       job.d_text = img->d_text.ptr;
     }
-    /* carried cursor: DFA engines start chunk 0 from its state, the filter engine sees its string as a virtual prefix */
-    if (t.engine == ACM_B200_ENGINE_FILTER) {
-      if (from->depth > 1024)
-        return finish (fail (ACM_B200_ERR_INVALID, "cursor deeper than 1024 symbols%s", ""));
-      job.prefix_len = from->depth;
-      uint32_t k = from->depth;
-      for (const ACState *s = from; s->parent; s = s->parent)
-        img->h_small->prefix[--k] = acm_symbol_of_state (m, s);
-    } else
-      job.init_dfa_state = t.dfa_of_state[from->id];
-
-    switch (t.engine) {
-      case ACM_B200_ENGINE_DFA_SMEM:
-        rc = run_dfa<uint16_t, true> (m, img, job, &total, scan->matches_on_device, scan->matches);
-        break;
-      case ACM_B200_ENGINE_DFA_GLOBAL:
-        rc = run_dfa<uint32_t, false> (m, img, job, &total, scan->matches_on_device, scan->matches);
-        break;
-      default:
-        rc = w == 1 ? run_filter<1> (m, img, job, &total, scan->matches_on_device, scan->matches)
-                    : (w == 2 ? run_filter<2> (m, img, job, &total, scan->matches_on_device, scan->matches) : run_filter<4> (m, img, job, &total, scan->matches_on_device, scan->matches));
-    }
-    if (rc)
+    if ((rc = apply_cursor (job)) || (rc = run_engine (job, &total, scan->matches_on_device, scan->matches)))
       return finish (rc);
     const uint64_t got = std::min<uint64_t> (total, scan->capacity);
     TRY_LOCKED (cudaStreamSynchronize (st));
-    float ms = 0;
     if (!scan->text_on_device) {
+      float ms = 0;
       cudaEventElapsedTime (&ms, img->ev[4], img->ev[5]);
       stats.h2d_ms = ms;
     }
-    cudaEventElapsedTime (&ms, img->ev[0], img->ev[3]);
-    stats.scan_kernel_ms = ms;
-    float a = 0, b = 0;
-    cudaEventElapsedTime (&a, img->ev[0], img->ev[1]);
-    if (t.engine != ACM_B200_ENGINE_FILTER)
-      cudaEventElapsedTime (&b, img->ev[2], img->ev[3]);
-    stats.main_kernel_ms = a + b;
+    add_kernel_times ();
     if (got && !scan->matches_on_device) {
       const auto c0 = std::chrono::steady_clock::now ();
       TRY_LOCKED (cudaMemcpyAsync (scan->matches, job.d_matches, got * sizeof (ACMB200Match), cudaMemcpyDeviceToHost, st));
       TRY_LOCKED (cudaStreamSynchronize (st));
       stats.d2h_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - c0).count ();
     }
-    /* cursor out */
-    if (scan->cursor) {
-      const uint64_t tail = std::min<uint64_t> (scan->nb_symbols, m->max_depth);
-      std::vector<unsigned char> buf (tail * w + 1);
-      const unsigned char *src = reinterpret_cast<const unsigned char *> (scan->text) + (scan->nb_symbols - tail) * w;
-      if (scan->text_on_device) {
-        TRY_LOCKED (cudaMemcpy (buf.data (), src, tail * w, cudaMemcpyDeviceToHost));
-        src = buf.data ();
+  } else if (scan->nb_symbols) {
+    /* ---- streaming ingest of host text: the text goes through two bounded device buffers; the copy of chunk
+     * i+1 (copy stream) overlaps the scan of chunk i.  Every chunk after the first is copied with max depth - 1 symbols of left
+     * context and scanned with that lead, exactly like a shard, so the records equal those of a single run. ---- */
+    const uint64_t chunk_syms = std::max<uint64_t> (stream_bytes / w / 4096 * 4096, 4096);
+    const uint64_t seg_lead = ((uint64_t)(m->max_depth ? m->max_depth - 1 : 0) + 15) / 16 * 16;
+    const unsigned char *host = reinterpret_cast<const unsigned char *> (scan->text);
+    DevBuf *bufs[2] = { &img->d_text, &img->d_text2 };
+    for (DevBuf *bf : bufs)
+      if ((rc = bf->ensure ((chunk_syms + seg_lead) * w + 64)))
+        return finish (rc);
+    const uint64_t nchunks = (scan->nb_symbols + chunk_syms - 1) / chunk_syms;
+    auto copy_chunk = [&] (uint64_t i) -> cudaError_t {
+      const uint64_t start = i * chunk_syms, lead = i ? seg_lead : 0, len = std::min<uint64_t> (chunk_syms, scan->nb_symbols - start);
+      cudaError_t e = cudaMemcpyAsync (bufs[i & 1]->ptr, host + (start - lead) * w, (len + lead) * w, cudaMemcpyHostToDevice, img->copy_stream);
+      return e != cudaSuccess ? e : cudaEventRecord (img->ev_copy[i & 1], img->copy_stream);
+    };
+    const auto h0 = std::chrono::steady_clock::now ();
+    TRY_LOCKED (copy_chunk (0));
+    uint64_t produced = 0;
+    for (uint64_t i = 0; i < nchunks; i++) {
+      const uint64_t start = i * chunk_syms, lead = i ? seg_lead : 0, len = std::min<uint64_t> (chunk_syms, scan->nb_symbols - start);
+      TRY_LOCKED (cudaStreamWaitEvent (st, img->ev_copy[i & 1], 0));
+      if (i + 1 < nchunks) /* the other buffer was last read by the scan of chunk i-1, which has completed */
+        TRY_LOCKED (copy_chunk (i + 1));
+      ScanJob job = {};
+      job.d_text = bufs[i & 1]->ptr;
+      job.n = len + lead;
+      job.lead = i ? std::max<uint64_t> (lead, scan->lead > start - lead ? scan->lead - (start - lead) : 0) : scan->lead;
+      job.base = scan->base + (start - lead);
+      job.capacity = scan->capacity > produced ? scan->capacity - produced : 0;
+      job.st = st;
+      if (i == 0 && (rc = apply_cursor (job)))
+        return finish (rc);
+      uint64_t seg_total = 0;
+      if ((rc = run_engine (job, &seg_total, false, nullptr)))
+        return finish (rc);
+      TRY_LOCKED (cudaStreamSynchronize (st));
+      add_kernel_times ();
+      const uint64_t got = std::min<uint64_t> (seg_total, job.capacity);
+      if (got) {
+        TRY_LOCKED (cudaMemcpyAsync (scan->matches + produced, job.d_matches, got * sizeof (ACMB200Match),
+                                     scan->matches_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        TRY_LOCKED (cudaStreamSynchronize (st));
       }
-      *scan->cursor = advance_cursor (m, from, src, tail, scan->nb_symbols < m->max_depth);
+      produced += got;
+      total += seg_total;
     }
+    stats.h2d_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - h0).count (); /* whole pipeline, copies overlapped */
+  }
+  /* cursor out */
+  if (scan->nb_symbols && scan->cursor) {
+    const uint64_t tail = std::min<uint64_t> (scan->nb_symbols, m->max_depth);
+    std::vector<unsigned char> buf (tail * w + 1);
+    const unsigned char *src = reinterpret_cast<const unsigned char *> (scan->text) + (scan->nb_symbols - tail) * w;
+    if (scan->text_on_device) {
+      TRY_LOCKED (cudaMemcpy (buf.data (), src, tail * w, cudaMemcpyDeviceToHost));
+      src = buf.data ();
+    }
+    *scan->cursor = advance_cursor (m, from, src, tail, scan->nb_symbols < m->max_depth);
   }
   stats.last_nb_symbols = scan->nb_symbols;
   stats.last_nb_matches = total;

@@ -49,7 +49,9 @@ enum { /* scan engines, chosen at finalise; see DESIGN.md */
 };
 
 typedef struct {
-  const void *text;        /* nb_symbols symbols of acm_b200_symbol_width() bytes each; host or device memory */
+  const void *text;        /* nb_symbols symbols of acm_b200_symbol_width() bytes each; host or device memory.  Host text larger than
+                              "stream_bytes" is streamed through two bounded device buffers, copy of chunk i+1 overlapping the scan of chunk i
+                              (pinned host memory makes the copies asynchronous) */
   uint64_t nb_symbols;
   uint64_t lead;           /* the first `lead` symbols are left context only: occurrences ENDING inside them are not reported.
                               A shard [a,b) of a larger text is scanned as text+a-lead with lead = min(a, acm_b200_max_keyword_length()-1) */
@@ -116,7 +118,8 @@ uint32_t acm_b200_max_keyword_length (const ACMachine *machine);
  * keyword get id 0).  The ids are what acm_b200_scan consumes for such machines. */
 int acm_b200_remap_text (ACMachine *machine, const void *letters, size_t letter_size, uint64_t nb, uint32_t *class_ids);
 
-/* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "tile_rows", "bloom_words", "bloom_k", "threads". */
+/* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "tile_rows", "bloom_words", "bloom_k", "threads";
+ * "stream_bytes" = size of the chunks host text is streamed in (default 256 MiB; host texts up to that size are copied whole). */
 int acm_b200_set_option (ACMachine *machine, const char *key, const char *value);
 int acm_b200_get_stats (ACMachine *machine, ACMB200Stats *stats);
 const char *acm_b200_last_error (void);

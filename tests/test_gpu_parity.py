@@ -178,3 +178,32 @@ def test_custom_comparator_machine_through_c_abi(tmp_path, novel):
     r = subprocess.run([str(exe), str(txt)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("records identical") == 4 and "width 4" in r.stdout
+
+
+@pytest.mark.parametrize("engine", ["dfa_smem", "dfa_global", "filter"])
+def test_streaming_ingest_equals_single_run(engine):
+    """Host text larger than the streaming threshold goes through two bounded device buffers in chunks (each re-copied with
+    max depth - 1 symbols of left context); records, their order, leads and the carried cursor must equal a single run's."""
+    words = [b"he", b"she", b"his", b"hers", b"ushers", b"pencil", b"abcdefghijklmnopqrstuvwxyz"]
+    rng = np.random.default_rng(8)
+    pieces = [b"To ushers: he found his pencil, but she could not find hers. ", b"abcdefghijklmnopqrstuvwxyz", b"xx", b"shershe"]
+    text = b"".join(pieces[i] for i in rng.integers(0, len(pieces), size=60_000))
+    text = np.frombuffer(text, dtype=np.uint8)
+    o = pyoracle.Oracle(best_oracle_kind(), 1)
+    o.insert_many(words)
+    want1 = o.scan(text[:1000], cap=1 << 22)
+    want2 = o.scan(text[1000:], base=1000, cap=1 << 23)  # cursor carried
+    m = ac75().Machine(1)
+    m.insert_many(words)
+    m.set_option("engine", engine)
+    m.set_option("stream_bytes", 256 * 1024)  # ~2.3 MB of text -> 9 chunks
+    got1 = m.scan(text[:1000], carry=True, capacity=1 << 22)
+    got2 = m.scan(text[1000:], base=1000, carry=True, capacity=1 << 23)
+    assert np.array_equal(got1, want1) and len(want2) > 100_000 and np.array_equal(got2, want2), (engine, len(got2), len(want2))
+    # a lead that spans several chunks, as a shard with a long left context would have
+    lead = 700_000
+    got3 = m.scan(text, lead=lead, capacity=1 << 23)
+    o.reset_cursor()
+    want3 = o.scan(text, cap=1 << 23)
+    assert np.array_equal(got3, want3[want3["end"] >= lead])
+    m.close(), o.close()
