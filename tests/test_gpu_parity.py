@@ -207,3 +207,42 @@ def test_streaming_ingest_equals_single_run(engine):
     want3 = o.scan(text, cap=1 << 23)
     assert np.array_equal(got3, want3[want3["end"] >= lead])
     m.close(), o.close()
+
+
+def test_batch_api_error_codes():
+    """The batch ABI reports misuse through return codes (the legacy API keeps the reference's ACM_ASSERT convention)."""
+    import ctypes
+
+    import torch
+
+    pkg = ac75()
+    a, b = pkg.Machine(1), pkg.Machine(1)
+    a.insert_many([b"abc"]), b.insert_many([b"abc"])
+    # capacity too small: ERR_CAPACITY, the total is still reported and the first records are valid
+    out = np.zeros(2, dtype=pkg.MATCH_DTYPE)
+    text = np.frombuffer(b"abc" * 10, dtype=np.uint8)
+    from importlib import import_module
+
+    binding = import_module("ac75.binding")
+    s = binding._Scan(text=text.ctypes.data, nb_symbols=len(text), lead=0, base=0, text_on_device=0, matches_on_device=0, matches=out.ctypes.data, capacity=2,
+                      cursor=None, stream=None, sorted=1)
+    n = ctypes.c_uint64(0)
+    assert pkg.lib().acm_b200_scan_ex(a._m, ctypes.byref(s), ctypes.byref(n)) == 6 and n.value == 10
+    assert out.tolist() == [(2, 0, 3), (5, 0, 3)]
+    # lead larger than the text, null text with symbols: ERR_INVALID
+    s.lead = len(text) + 1
+    assert pkg.lib().acm_b200_scan_ex(a._m, ctypes.byref(s), ctypes.byref(n)) == 1
+    s.lead, s.text = 0, None
+    assert pkg.lib().acm_b200_scan_ex(a._m, ctypes.byref(s), ctypes.byref(n)) == 1
+    # a cursor of another machine: ERR_INVALID
+    s.text = text.ctypes.data
+    foreign = ctypes.c_void_p(pkg.lib().acm_initiate(b._m))
+    s.cursor = ctypes.pointer(foreign)
+    assert pkg.lib().acm_b200_scan_ex(a._m, ctypes.byref(s), ctypes.byref(n)) == 1
+    # misaligned device text: ERR_INVALID
+    d = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.AcmError) as e:
+        a.scan_device(d.data_ptr() + 1, 100)
+    assert e.value.code == 1
+    assert a.scan_device(d.data_ptr(), 1024) == 0
+    a.close(), b.close()
