@@ -244,13 +244,15 @@ def main():
     def step_device():
         return m.scan_device(d_text.data_ptr(), n, lead=lead, base=first, d_matches_ptr=d_matches.data_ptr(), capacity=cap, stream=stream.cuda_stream)
 
+    counts_in = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+    counts_all = torch.zeros(world, dtype=torch.int64, device="cuda")
+
     def exchange(local_count):
         if world == 1:
             return local_count
-        t = torch.tensor([local_count], dtype=torch.int64, device="cuda")
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t)  # the path's only collective: one match count per GPU
-        return int(sum(int(x.item()) for x in out))
+        counts_in[0] = local_count
+        dist.all_gather_into_tensor(counts_all, counts_in.cuda(non_blocking=True))  # the path's only collective: one match count per GPU
+        return int(counts_all.sum().item())
 
     def barrier():
         if world > 1:

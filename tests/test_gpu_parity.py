@@ -246,3 +246,16 @@ def test_batch_api_error_codes():
     assert e.value.code == 1
     assert a.scan_device(d.data_ptr(), 1024) == 0
     a.close(), b.close()
+
+
+@pytest.mark.parametrize("engine", ["filter", "dfa_global", "auto"])
+def test_all_ones_and_zero_bytes(engine):
+    """Keys made of 0xFF / 0x00 bytes: 0xFFFFFFFF is the empty marker of the filter's compact key set and must still be found."""
+    words = [b"\xff\xff\xff\xff", b"\xff\xff\xff\xff\xff\xff", b"\x00\x00\x00\x00", b"\x00\xff\x00\xff", b"\xff\x00\x00\x00\x00\xff"]
+    rng = np.random.default_rng(3)
+    text = rng.choice(np.array([0, 255], dtype=np.uint8), size=300_000, p=[0.5, 0.5])
+    text[1000:1100] = 255
+    text[5000:5100] = 0
+    want = oracle_records(words, text=text)
+    got, st = gpu_scan(words, text=text, engine=engine)
+    assert len(want) > 10_000 and np.array_equal(got, want), (engine, st["engine"], len(got), len(want))
