@@ -247,12 +247,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
   if (!strcmp (key, "engine")) {
     snprintf (m->engine_override, sizeof m->engine_override, "%s", strcmp (value, "auto") ? value : "");
     m->generation++; /* forces a rebuild */
-  } else if (!strcmp (key, "tile_rows"))
-    m->option_tile_rows = strtoull (value, 0, 10);
-  else if (!strcmp (key, "bloom_words"))
+  } else if (!strcmp (key, "bloom_words"))
     m->option_bloom_words = strtoull (value, 0, 10), m->generation++;
-  else if (!strcmp (key, "bloom_k"))
-    m->option_bloom_k = strtoull (value, 0, 10), m->generation++;
   else if (!strcmp (key, "threads"))
     m->option_threads = strtoull (value, 0, 10);
   else if (!strcmp (key, "stream_bytes"))
@@ -393,7 +389,7 @@ static int
 run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool dense, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily, uint64_t *total,
                  ACMB200Match **out_used, bool first_segment, bool last_segment) {
   const acm_tables &t = img->tab;
-  const int kRowsOpt = m->option_tile_rows == 2 ? 2 : 4; /* rows of 512 bytes per warp tile (tuning knob) */
+  constexpr int kRowsOpt = 4; /* rows of 512 bytes per warp tile; 2 and 8 were measured slower */
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
   {
     FilterParams p = {};
@@ -449,16 +445,16 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
 
     void (*f1) (const FilterParams) = nullptr;
     const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
-    const int K = t.bloom_k > 2 ? 3 : 2;
+    const int K = 2; /* bits per key; 3 was measured slower, the kernels keep K as a template parameter */
 #define ACM_F1_(Q_, K_, R_)                                                                                                                      \
   (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, true> : filter_scan_kernel<W, R_, Q_, K_, false, true>)       \
             : (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, false> : filter_scan_kernel<W, R_, Q_, K_, false, false>))
 #define ACM_F1(Q_, K_)                                                                                                                           \
   if (p.q == Q_ && K == K_)                                                                                                                      \
-    f1 = kRowsOpt == 2 ? ACM_F1_ (Q_, K_, 2) : ACM_F1_ (Q_, K_, 4)
-    ACM_F1 (1, 2); ACM_F1 (1, 3); ACM_F1 (2, 2); ACM_F1 (2, 3);
+    f1 = ACM_F1_ (Q_, K_, kRowsOpt)
+    ACM_F1 (1, 2); ACM_F1 (2, 2);
     if (W == 1) {
-      ACM_F1 (3, 2); ACM_F1 (3, 3); ACM_F1 (4, 2); ACM_F1 (4, 3);
+      ACM_F1 (3, 2); ACM_F1 (4, 2);
     }
 #undef ACM_F1
 #undef ACM_F1_

@@ -422,11 +422,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
   if (want_words < 64)
     want_words = 64;
   t->bloom_words = (uint32_t)want_words;
-  t->bloom_k = m->option_bloom_k ? (uint32_t)m->option_bloom_k : 2;
-  if (t->bloom_k > 3)
-    t->bloom_k = 3;
-  if (t->bloom_k < 2)
-    t->bloom_k = 2;
+  t->bloom_k = 2; /* bits per key: 3 lowers the false-positive rate but costs more than it saves */
   t->bloom = calloc (t->bloom_words, sizeof (uint32_t));
   if (!t->bloom)
     goto done;

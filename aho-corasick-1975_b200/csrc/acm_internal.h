@@ -86,7 +86,7 @@ struct _ac_machine {
   struct acm_device_image *device;
   uint64_t device_generation;
   char engine_override[16];
-  uint64_t option_tile_rows, option_bloom_words, option_bloom_k, option_threads, option_stream_bytes;
+  uint64_t option_bloom_words, option_threads, option_stream_bytes;
 };
 
 /* acm_host.c */

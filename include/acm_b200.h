@@ -118,7 +118,7 @@ uint32_t acm_b200_max_keyword_length (const ACMachine *machine);
  * keyword get id 0).  The ids are what acm_b200_scan consumes for such machines. */
 int acm_b200_remap_text (ACMachine *machine, const void *letters, size_t letter_size, uint64_t nb, uint32_t *class_ids);
 
-/* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "tile_rows", "bloom_words", "bloom_k", "threads";
+/* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "bloom_words", "threads";
  * "stream_bytes" = size of the chunks host text is streamed in (default 256 MiB; host texts up to that size are copied whole). */
 int acm_b200_set_option (ACMachine *machine, const char *key, const char *value);
 int acm_b200_get_stats (ACMachine *machine, ACMB200Stats *stats);
