@@ -88,16 +88,19 @@ struct acm_device_image {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
   DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
     uint32_t overflow;
     uint32_t pad;
+    unsigned long long span_counter;
+    uint64_t pad2;
     uint32_t prefix[1024];
   } *h_small = nullptr;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
+  bool stride2 = false;   /* the stride-2 tables (bloom_s2, pairbits) are resident */
   ACMB200Stats stats = {};
 };
 
@@ -106,7 +109,7 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_text2, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_text2, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
@@ -177,7 +180,10 @@ finalise_locked (ACMachine *m, int device) {
   acm_free_tables (&img->tab);
   /* shared-memory budget for the resident table: everything a block may opt in to, minus class map / staging / slack */
   const uint64_t budget = img->smem_optin - 32 * (192 * 2 + 16) - 2048;
-  int rc = acm_build_tables (m, &img->tab, budget);
+  /* the stride-2 kernel works best when it leaves part of the SM's 256 KB to the L1 cache (its confirmation step re-reads text the
+   * tile loads brought in): by default it takes the 196 KB carve-out, not the largest one */
+  const uint64_t s2_smem = m->option_s2_smem_kb ? std::min<uint64_t> (img->smem_optin, m->option_s2_smem_kb * 1024 - 1024) : std::min<uint64_t> (img->smem_optin, 195 * 1024);
+  int rc = acm_build_tables (m, &img->tab, budget, m->option_no_stride2 ? 0 : s2_smem);
   if (rc)
     return fail (rc, "building the automaton tables failed%s", "");
   acm_tables &t = img->tab;
@@ -187,11 +193,12 @@ finalise_locked (ACMachine *m, int device) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (t.bloom2 && (rc = upload (img->d_bloom2, t.bloom2, (size_t)t.bloom2_words * 4, st))) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
         || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
         || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
+        || (t.bloom_s2 && ((rc = upload (img->d_bloom_s2, t.bloom_s2, (size_t)t.bloom_s2_words * 4, st)) || (rc = upload (img->d_pairbits, t.pairbits, (size_t)4 << t.pairbits_log2, st))))
         || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
         || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st)))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot) + t.kw_pool_bytes + (uint64_t)t.nb_keywords * 12
-            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0);
+            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0) + (t.bloom_s2 ? (uint64_t)t.bloom_s2_words * 4 + ((uint64_t)4 << t.pairbits_log2) : 0);
   } else {
     if ((rc = upload (img->d_delta, t.delta, t.delta_bytes, st)) || (rc = upload (img->d_out_offsets, t.out_offsets, ((size_t)t.nb_dfa_states - t.out_threshold + 1) * 4, st))
         || (rc = upload (img->d_out_entries, t.out_entries, t.nb_out_entries * sizeof (acm_output), st)))
@@ -206,6 +213,9 @@ finalise_locked (ACMachine *m, int device) {
   free (t.bloom), t.bloom = nullptr;
   img->two_level = t.bloom2 != nullptr;
   free (t.bloom2), t.bloom2 = nullptr;
+  img->stride2 = t.bloom_s2 != nullptr;
+  free (t.bloom_s2), t.bloom_s2 = nullptr;
+  free (t.pairbits), t.pairbits = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
   free (t.qset), t.qset = nullptr;
   free (t.kw_len), t.kw_len = nullptr;
@@ -222,7 +232,8 @@ finalise_locked (ACMachine *m, int device) {
   s.min_keyword_length = t.lmin;
   s.nb_classes = t.nb_classes;
   s.table_bytes = bytes;
-  s.filter_fp = t.engine == ACM_B200_ENGINE_FILTER ? t.bloom_fp : 0;
+  s.filter_fp = t.engine == ACM_B200_ENGINE_FILTER ? (img->stride2 ? t.bloom_s2_hit_rate : t.bloom_fp) : 0;
+  s.filter_stride = 0;
   s.finalise_count++;
   s.finalise_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count ();
   return ACM_B200_OK;
@@ -253,6 +264,10 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_threads = strtoull (value, 0, 10);
   else if (!strcmp (key, "stream_bytes"))
     m->option_stream_bytes = strtoull (value, 0, 10);
+  else if (!strcmp (key, "s2_smem_kb"))
+    m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++;
+  else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
+    m->option_no_stride2 = !strtoull (value, 0, 10), m->generation++;
   else
     rc = ACM_B200_ERR_INVALID;
   acm_unlock (m);
@@ -398,8 +413,15 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.lead = job.lead;
     p.base = job.base;
     p.q = t.q;
-    p.tile_syms = kRowsOpt * 512 / W;
+    const bool s2 = W == 1 && !dense && img->stride2; /* stride-2 kernel: its "tiles" for F2..F4 are spans of 2 KiB tiles */
+    p.tile_syms = s2 ? kS2SpanBytes : kRowsOpt * 512 / W;
     p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
+    p.bloom_s2 = img->d_bloom_s2.as<uint32_t> ();
+    p.bloom_s2_words = t.bloom_s2_words;
+    p.pairbits = img->d_pairbits.as<uint32_t> ();
+    p.pairbits_log2 = t.pairbits_log2;
+    p.span_counter = &d_small->span_counter;
+    p.s2_hit_cap = t.s2_hit_cap;
     p.bloom = img->d_bloom.as<uint32_t> ();
     p.bloom_words = t.bloom_words;
     p.bloom_k = t.bloom_k;
@@ -425,7 +447,9 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     int warps = 32;
     while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
       warps /= 2;
-    const size_t smem = (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp;
+    if (s2)
+      warps = 32;
+    const size_t smem = s2 ? (size_t)t.bloom_s2_words * 4 + 32 * (size_t)ACM_S2_WARP_BYTES (t.s2_hit_cap) : (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp;
     if (smem > img->smem_optin)
       return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
     int rc;
@@ -458,16 +482,20 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     }
 #undef ACM_F1
 #undef ACM_F1_
+    if (s2) /* 2 bits per key, 3 x 32 hits confirmed at a time, 4 rows per tile: the measured optimum */
+      f1 = filter_scan_s2_kernel<2, 3, 4>;
     if (!f1)
       return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
     CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     img->stats.smem_bytes = smem;
+    img->stats.filter_stride = s2 ? 2 : 1;
     /* header of Small (cand_count, grand_total, overflow) cleared; the prefix symbols follow */
     img->h_small->cand_count = 0;
     img->h_small->grand_total = 0;
     img->h_small->overflow = 0;
+    img->h_small->span_counter = 0;
     CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
-    const unsigned grid = (unsigned)std::min<uint64_t> ((p.ntiles + warps - 1) / warps, (uint64_t)img->sm_count);
+    const unsigned grid = (unsigned)std::min<uint64_t> (((s2 ? (job.n + 2047) / 2048 : p.ntiles) + warps - 1) / warps, (uint64_t)img->sm_count);
     if (first_segment)
       CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
     f1<<<grid, warps * 32, smem, job.st>>> (p);

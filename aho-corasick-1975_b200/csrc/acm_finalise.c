@@ -159,6 +159,8 @@ acm_free_tables (struct acm_tables *t) {
   free (t->dfa_of_state);
   free (t->bloom);
   free (t->bloom2);
+  free (t->bloom_s2);
+  free (t->pairbits);
   free (t->qgrams);
   free (t->qset);
   free (t->kw_len);
@@ -263,7 +265,7 @@ build_dfa (struct _ac_machine *m, struct acm_tables *t, struct _ac_state **by_de
  * node but to a "tail" (ACM_TAIL_FLAG | keyword id): the rest of that keyword is compared directly against the text from the
  * keyword pool.  Only edges leaving nodes with two or more keywords below them are stored. */
 static int
-build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget) {
+build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget, uint64_t smem_optin) {
   const uint32_t nk = (uint32_t)m->nb_sequences;
   uint64_t total_syms = 0;
   for (uint32_t r = 0; r < nk; r++)
@@ -452,6 +454,72 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget)
     }
     t->bloom_fp *= fp2 / t->bloom2_words;
   }
+  /* stride-2 filter (acm_tables.h): byte alphabet, every keyword at least 4 bytes long, dictionary small enough for the
+   * shared-memory level to stay selective with two keys per keyword */
+  if (t->width == 1 && q == 4 && nk && !t->bloom2 && smem_optin >= 65536) {
+    /* smem_optin here = the shared memory the stride-2 kernel may use in total (filter + per-warp stages).  The stage capacity
+     * depends on the hit rate, which depends on the filter size: start from a small stage and grow it until it fits. */
+    const uint8_t *pool = t->kw_pool;
+    const uint32_t s2k = 2; /* bits per key; 3 was measured slower at every filter size */
+    uint32_t *bl = 0;
+    uint32_t words = 0, hit_cap = 96;
+    double hit_rate = 1;
+    for (int attempt = 0; attempt < 8; attempt++, hit_cap += 32) {
+      const uint64_t room = smem_optin - 2048;
+      if (room < 32ull * ACM_S2_WARP_BYTES (hit_cap) + 4096)
+        break;
+      const uint64_t s2_max = (room - 32ull * ACM_S2_WARP_BYTES (hit_cap)) / 4;
+      uint64_t s2_want = m->option_bloom_words ? m->option_bloom_words : pow2_at_least ((2ull * nk * 24 + 31) / 32);
+      if (s2_want > s2_max)
+        s2_want = s2_max;
+      if (s2_want < 64)
+        s2_want = 64;
+      if (!bl || (uint32_t)s2_want != words) {
+        free (bl);
+        words = (uint32_t)s2_want;
+        bl = calloc (words, sizeof (uint32_t));
+        if (!bl)
+          goto done;
+        for (uint32_t r = 0; r < nk; r++) {
+          const uint8_t *k = pool + t->kw_off[r] + t->kw_len[r] - 4; /* the last four bytes */
+          const uint32_t a = acm_s2_key (k[1], k[2], k[3]), b = acm_s2_key (k[0], k[1], k[2]);
+          bl[acm_bloom_word (a, words)] |= acm_bloom_mask (a, s2k);
+          bl[acm_bloom_word (b, words)] |= acm_bloom_mask (b, s2k);
+        }
+        double fp2 = 0;
+        for (uint32_t i = 0; i < words; i++) {
+          const double f = __builtin_popcount (bl[i]) / 32.0;
+          fp2 += s2k > 2 ? f * f * f : f * f;
+        }
+        hit_rate = fp2 / words + 2.0 * nk / 16777216.0;
+      }
+      if (hit_rate * 1024 * 1.5 + 32 <= hit_cap) { /* expected hits per tile (1024 tests) leave a 1.5x margin in the stage */
+        uint32_t lg = 16;
+        while (lg < 24 && (1ull << lg) < 32ull * nk)
+          lg++;
+        t->pairbits = calloc ((size_t)1 << lg, sizeof (uint32_t));
+        if (!t->pairbits) {
+          free (bl);
+          goto done;
+        }
+        t->pairbits_log2 = lg;
+        for (uint32_t r = 0; r < nk; r++) {
+          const uint8_t *k = pool + t->kw_off[r] + t->kw_len[r] - 4;
+          const uint32_t win4 = k[0] | ((uint32_t)k[1] << 8) | ((uint32_t)k[2] << 16) | ((uint32_t)k[3] << 24);
+          t->pairbits[acm_pair_word (win4 >> 8, lg)] |= acm_pair_mask (win4, 0);         /* ends on the sampled position */
+          t->pairbits[acm_pair_word (win4 & 0xFFFFFFu, lg)] |= acm_pair_mask (win4, 1);  /* ends one after it */
+        }
+        t->bloom_s2 = bl;
+        t->bloom_s2_words = words;
+        t->bloom_s2_k = s2k;
+        t->bloom_s2_hit_rate = hit_rate;
+        t->s2_hit_cap = hit_cap;
+        bl = 0;
+        break;
+      }
+    }
+    free (bl);
+  }
   rc = ACM_B200_OK;
 done:
   free (full);
@@ -467,7 +535,7 @@ done:
 
 /* ---- entry ---------------------------------------------------------------------------------------------------------- */
 int
-acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget) {
+acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget, uint64_t smem_optin) {
   memset (t, 0, sizeof (*t));
   const uint32_t n = (uint32_t)m->nb_states;
   t->nb_states = n;
@@ -528,7 +596,7 @@ acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_bud
 
   int rc;
   if (engine == ACM_B200_ENGINE_FILTER)
-    rc = build_filter (m, t, smem_budget);
+    rc = build_filter (m, t, smem_budget, smem_optin);
   else {
     t->delta_entry_bytes = engine == ACM_B200_ENGINE_DFA_SMEM ? 2 : 4;
     /* states sorted by depth (counting sort) */

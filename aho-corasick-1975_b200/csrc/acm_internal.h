@@ -87,6 +87,8 @@ struct _ac_machine {
   uint64_t device_generation;
   char engine_override[16];
   uint64_t option_bloom_words, option_threads, option_stream_bytes;
+  int option_no_stride2;
+  uint64_t option_s2_smem_kb;
 };
 
 /* acm_host.c */

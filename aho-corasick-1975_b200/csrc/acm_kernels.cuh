@@ -20,6 +20,7 @@
 #include "acm_b200.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace acm {
 
@@ -418,6 +419,14 @@ struct FilterParams {
   const uint64_t *tile_offsets;
   ACMB200Match *matches;
   uint64_t capacity;
+  /* stride-2 kernel (F1s): its filter, its second level, and the spans it works in.  With this kernel the "tiles" of F2..F4
+   * (tile_syms, ntiles, tile_first, tile_n) are the spans. */
+  const uint32_t *bloom_s2;
+  uint32_t bloom_s2_words;
+  const uint32_t *pairbits;
+  uint32_t pairbits_log2;
+  uint32_t s2_hit_cap;
+  unsigned long long *span_counter;
 };
 
 template <int W> struct SymT;
@@ -800,6 +809,303 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
     if (lane == 0) {
       p.tile_first[tile] = first;
       p.tile_n[tile] = kept;
+    }
+    __syncwarp ();
+  }
+}
+
+/* F1s: the stride-2 variant of F1 for byte alphabets whose shortest keyword has at least 4 bytes (acm_tables.h).
+ *
+ * Only the even offsets of a tile are tested, each on the 3-byte window ending there: 8 tests per lane and 512-byte row instead
+ * of 16, built with one byte permute each (one shared-memory lookup per TWO text bytes).  A hit at the sampled position s names two
+ * candidate end positions, s and s+1.  Hits are staged as (lane, test index), slots from a warp scan; the confirmation step re-reads
+ * the 5 bytes s-3..s+1 (usually still in L1: the tile loads are evict_last and the kernel leaves ~60 KB of the SM to L1), loads ONE
+ * word of the second-level table (L2, ld.global.cg; indexed by the 3-byte window, two bits per role and 4-byte window) and keeps the
+ * few survivors.  A warp works through a span of consecutive tiles taken from a global counter and appends the span's candidates, in
+ * position order, with one reservation -- so F2..F4 see spans where they saw tiles.  F2 verifies candidates exactly, so everything
+ * here may err on the side of keeping a position; nothing may drop one.
+ * Measured cost split on config 3: filter tests 2.1 ms per 8 GiB, staging 0.4 ms, confirmation 1.2 ms. */
+constexpr uint32_t kS2SpanBytes = 32768;
+
+template <int K, int kBatches, int kRows>
+__global__ void __launch_bounds__ (1024, 1)
+filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
+  constexpr uint32_t kTileBytes = kRows * 512;
+  constexpr int kAcc = (kRows + 3) / 4;       /* 32 verdict bits per accumulator: 8 tests per row */
+  constexpr int kAccShift = kRows < 4 ? 32 - 8 * kRows : 0; /* fewer than 32 tests: move the verdicts to the top bits */
+  constexpr uint32_t kSpanTiles = kS2SpanBytes / kTileBytes;
+  extern __shared__ __align__ (16) unsigned char smem[];
+  uint32_t *s_bloom = reinterpret_cast<uint32_t *> (smem);
+  for (uint32_t i = threadIdx.x; i < p.bloom_s2_words; i += blockDim.x)
+    s_bloom[i] = p.bloom_s2[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t kHitCap = p.s2_hit_cap; /* 1.5x the expected hits per tile + 32, see acm_finalise.c */
+  unsigned char *mine = smem + (size_t)p.bloom_s2_words * 4 + (size_t)warp * ACM_S2_WARP_BYTES (kHitCap);
+  uint16_t *hits = reinterpret_cast<uint16_t *> (mine + 16);
+  uint32_t *cands = reinterpret_cast<uint32_t *> (mine + 16 + kHitCap * 2);
+  __syncthreads ();
+
+  const uint32_t nwords = p.bloom_s2_words;
+  const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
+  const uint32_t pair_shift = 32 - p.pairbits_log2;
+  const uint64_t first_end = max (p.lead, (uint64_t)3); /* ends before it: none without a carried prefix, else listed below */
+  const uint64_t ntiles = (p.n + kTileBytes - 1) / kTileBytes;
+  uint4 v[kRows];
+  uint32_t before_tile = 0;
+  auto interior_tile = [&] (uint64_t t) { return t * kTileBytes >= first_end + 1 && (t + 1) * kTileBytes <= p.n; };
+  auto load_tile = [&] (uint64_t t) {
+    const uint64_t base = t * kTileBytes;
+    const uint8_t *ptr = text8 + base;
+    if (interior_tile (t)) {
+#pragma unroll
+      for (int r = 0; r < kRows; r++) /* evict_last: the confirmation step re-reads a few words of the tile one iteration later */
+        asm volatile ("ld.global.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "l"(ptr + r * 512 + lane * 16));
+      before_tile = *reinterpret_cast<const uint32_t *> (ptr - 4);
+    } else { /* first / last tile: bytes outside the text read as zero */
+#pragma unroll
+      for (int r = 0; r < kRows; r++) {
+        const uint64_t byte0 = base + (uint64_t)r * 512 + (uint64_t)lane * 16;
+        if (byte0 + 16 <= p.n)
+          v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
+        else {
+          uint32_t w[4] = { 0, 0, 0, 0 };
+          for (int i = 0; i < 16; i++)
+            if (byte0 + i < p.n)
+              w[i >> 2] |= (uint32_t)text8[byte0 + i] << (8 * (i & 3));
+          v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
+        }
+      }
+      before_tile = base >= 4 ? *reinterpret_cast<const uint32_t *> (ptr - 4) : 0;
+    }
+  };
+
+  for (;;) {
+    unsigned long long span = 0;
+    if (lane == 0)
+      span = atomicAdd (p.span_counter, 1ull);
+    span = __shfl_sync (kFull, span, 0);
+    if (span >= p.ntiles)
+      break;
+    const uint64_t tile0 = span * kSpanTiles, tile1 = min (ntiles, tile0 + kSpanTiles);
+    uint32_t ncand = 0; /* warp-uniform: candidates of this span held in cands[], span-relative positions, ordered */
+    load_tile (tile0);
+
+    for (uint64_t tile = tile0; tile < tile1; tile++) {
+      const uint64_t tile_base = tile * kTileBytes;
+      const bool interior = interior_tile (tile);
+      const uint32_t tile_off = (uint32_t)(tile - tile0) * kTileBytes;
+      const uint32_t tile_first_cand = ncand;
+      if (tile + 2 < tile1 && lane < kRows * 4)
+        asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + (tile + 2) * kTileBytes + lane * 128));
+
+      /* ---- filter: 8 tests per lane and row, verdicts shifted into acc[] (test 0 of an accumulator ends at bit 31) ---- */
+      uint32_t acc[kAcc];
+#pragma unroll
+      for (int a = 0; a < kAcc; a++)
+        acc[a] = 0;
+      auto test = [&] (uint32_t key, uint32_t &dst) {
+        const unsigned long long p1 = (unsigned long long)key * ACM_BLOOM_C1;
+        const uint32_t lo = (uint32_t)p1, hi = (uint32_t)(p1 >> 32);
+        const uint32_t word = s_bloom[__umulhi (lo, nwords)];
+        uint32_t t = (word >> (hi & 31u)) & (word >> (lo & 31u));
+        if (K > 2)
+          t &= word >> (__umulhi (key, ACM_BLOOM_C2) & 31u);
+        t &= 1u;
+        asm ("mad.lo.u32 %0, %0, 2, %1;" : "+r"(dst) : "r"(t)); /* dst = 2 dst + verdict on the FMA pipe (kept out of the ALU-side LOP3 trees) */
+      };
+#pragma unroll
+      for (int r = 0; r < kRows; r++) {
+        const uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
+        const uint32_t wrap = r == 0 ? before_tile : __shfl_sync (kFull, v[r > 0 ? r - 1 : 0].w, 31);
+        const uint32_t w[5] = { lane == 0 ? wrap : up, v[r].x, v[r].y, v[r].z, v[r].w };
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          test (__byte_perm (w[j], w[j + 1], 0x4432), acc[r >> 2]); /* window ending at byte 4j of the lane's 16: two bytes of the word before */
+          test (__byte_perm (w[j + 1], 0u, 0x2210), acc[r >> 2]);   /* window ending at byte 4j+2 */
+        }
+      }
+
+      /* ---- stage the hits as (lane << 6) | test index; slots from a warp scan of the per-lane counts (a shared counter would
+       * serialise the ~28 lanes that have hits on one bank) ---- */
+      uint32_t staged;
+      {
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int a = 0; a < kAcc; a++)
+          cnt += __popc (acc[a]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync (kFull, incl, d);
+          if (lane >= d)
+            incl += o;
+        }
+        staged = __shfl_sync (kFull, incl, 31);
+        uint32_t at = incl - cnt;
+#pragma unroll
+        for (int a = 0; a < kAcc; a++) {
+          const uint32_t tag = ((uint32_t)lane << 6) | (a * 32);
+          uint32_t bits = acc[a] << kAccShift;
+          while (bits) {
+            const uint32_t ti = __clz (bits);
+            bits &= ~(0x80000000u >> ti);
+            if (at < kHitCap)
+              hits[at] = (uint16_t)(tag | ti);
+            at++;
+          }
+        }
+      }
+      if (tile + 1 < tile1)
+        load_tile (tile + 1); /* in flight during the confirmation below */
+      __syncwarp ();
+      if (staged > kHitCap) {
+        if (lane == 0)
+          atomicExch (p.overflow, 1u);
+        staged = kHitCap;
+      }
+
+      /* ends whose 4-byte window reaches into the carried-cursor prefix: kept unconditionally (F2 decides) */
+      if (tile == 0 && p.prefix_len) {
+        const uint64_t e = p.lead + lane;
+        const bool keep = e < min ((uint64_t)3, p.n);
+        const uint32_t m = __ballot_sync (kFull, keep);
+        if (keep)
+          cands[ncand + __popc (m & lanes_below)] = (uint32_t)e;
+        ncand += __popc (m);
+      }
+
+      /* ---- confirmation: up to kBatches x 32 hits in flight.  Interior tiles run straight-line code: every lane loads (idle lanes
+       * repeat the last hit) so that all text loads are issued before the first one is consumed, then all second-level loads. ---- */
+      auto confirm = [&] (auto nb_tag, uint32_t b) {
+        constexpr int kNb = decltype (nb_tag)::value;
+        uint32_t rel[kNb];
+        bool live[kNb], ok_a[kNb], ok_b[kNb];
+#pragma unroll
+        for (int u = 0; u < kNb; u++) {
+          const uint32_t i = b + 32 * u + lane;
+          live[u] = i < staged;
+          const uint32_t h = hits[min (i, staged - 1)], ti = h & 63u;
+          rel[u] = ((h >> 6) << 4) + ((ti >> 3) << 9) + ((ti & 7u) << 1); /* the sampled position, tile-relative */
+        }
+        if (interior) {
+          uint32_t t0[kNb], t1[kNb], word[kNb];
+          const uint8_t *tile_m4 = text8 + tile_base - 4; /* the tile is preceded by text */
+#pragma unroll
+          for (int u = 0; u < kNb; u++) { /* bytes s-3 .. s+1 from two aligned words */
+            const uint32_t *t32 = reinterpret_cast<const uint32_t *> (tile_m4 + (uint64_t)((rel[u] + 1u) & ~3u));
+            t0[u] = t32[0]; /* through L1: the tile's lines are often still there */
+            t1[u] = t32[1];
+          }
+#pragma unroll
+          for (int u = 0; u < kNb; u++) {
+            const uint32_t sh = 8u * ((rel[u] + 1u) & 3u); /* (s - 3) mod 4 = 1 or 3 */
+            const uint32_t k0 = __funnelshift_r (t0[u], t1[u], sh), k1 = __funnelshift_rc (t0[u], t1[u], sh + 8u);
+            word[u] = __ldcg (p.pairbits + (((k0 >> 8) * ACM_PAIR_C0) >> pair_shift)); /* L2 only: random words must not evict the tiles from L1 */
+            t0[u] = k0 * ACM_PAIR_CA;
+            t1[u] = k1 * ACM_PAIR_CB;
+          }
+#pragma unroll
+          for (int u = 0; u < kNb; u++) {
+            ok_a[u] = live[u] && ((word[u] >> (t0[u] >> 27)) & (word[u] >> ((t0[u] >> 22) & 31u)) & 1u) != 0;
+            ok_b[u] = live[u] && ((word[u] >> (t1[u] >> 27)) & (word[u] >> ((t1[u] >> 22) & 31u)) & 1u) != 0;
+          }
+        } else { /* first / last tile: every end is checked for its range, its window is read byte by byte */
+#pragma unroll
+          for (int u = 0; u < kNb; u++)
+#pragma unroll
+            for (int role = 0; role < 2; role++) {
+              const uint64_t e = tile_base + rel[u] + role;
+              bool ok = live[u] && e >= first_end && e < p.n;
+              if (ok) {
+                const uint32_t win4 = (uint32_t)text8[e - 3] | ((uint32_t)text8[e - 2] << 8) | ((uint32_t)text8[e - 1] << 16) | ((uint32_t)text8[e] << 24);
+                const uint32_t word = __ldg (p.pairbits + acm_pair_word (role ? (win4 & 0xFFFFFFu) : (win4 >> 8), p.pairbits_log2));
+                const uint32_t mask = acm_pair_mask (win4, role);
+                ok = (word & mask) == mask;
+              }
+              if (role)
+                ok_b[u] = ok;
+              else
+                ok_a[u] = ok;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kNb; u++) {
+          const uint32_t ma = __ballot_sync (kFull, ok_a[u]), mb = __ballot_sync (kFull, ok_b[u]);
+          if (ma | mb) { /* rare */
+            const uint32_t na = __popc (ma);
+            if (ok_a[u]) {
+              const uint32_t at = ncand + __popc (ma & lanes_below);
+              if (at < ACM_S2_CAND_CAP)
+                cands[at] = tile_off + rel[u];
+            }
+            if (ok_b[u]) {
+              const uint32_t at = ncand + na + __popc (mb & lanes_below);
+              if (at < ACM_S2_CAND_CAP)
+                cands[at] = tile_off + rel[u] + 1u;
+            }
+            ncand += na + __popc (mb);
+          }
+        }
+      };
+      {
+        uint32_t b = 0; /* full groups of kBatches batches, then what is left as one group of 2 or 1 (kBatches <= 3) */
+        static_assert (kBatches >= 1 && kBatches <= 3, "the remainder handling below covers at most two left-over batches");
+        for (; b + 32 * (kBatches - 1) < staged; b += 32 * kBatches)
+          confirm (std::integral_constant<int, kBatches> (), b);
+        if (kBatches > 2 && b + 32 < staged) {
+          confirm (std::integral_constant<int, 2> (), b);
+          b += 64;
+        }
+        if (kBatches > 1 && b < staged)
+          confirm (std::integral_constant<int, 1> (), b);
+      }
+      __syncwarp ();
+      if (ncand > ACM_S2_CAND_CAP) {
+        if (lane == 0)
+          atomicExch (p.overflow, 1u);
+        ncand = ACM_S2_CAND_CAP;
+      }
+      /* the tile's survivors were appended in staging order: sort them by position (rank = number of smaller ones) */
+      const uint32_t fresh = ncand - tile_first_cand;
+      if (fresh > 1) {
+        if (fresh > 32) {
+          if (lane == 0)
+            atomicExch (p.overflow, 1u);
+        } else {
+          const uint32_t mine_pos = (uint32_t)lane < fresh ? cands[tile_first_cand + lane] : 0xFFFFFFFFu;
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < fresh; j++)
+            rank += cands[tile_first_cand + j] < mine_pos;
+          __syncwarp ();
+          if ((uint32_t)lane < fresh)
+            cands[tile_first_cand + rank] = mine_pos;
+          __syncwarp ();
+        }
+      }
+    }
+
+    /* ---- one reservation per span ---- */
+    uint64_t first = 0;
+    if (ncand) {
+      unsigned long long seg = 0;
+      if (lane == 0)
+        seg = atomicAdd (p.cand_count, (unsigned long long)ncand);
+      seg = __shfl_sync (kFull, seg, 0);
+      if (seg + ncand > p.cand_cap) {
+        if (lane == 0)
+          atomicExch (p.overflow, 1u);
+        ncand = 0;
+      } else {
+        first = seg;
+        const uint64_t span_base = tile0 * kTileBytes;
+        for (uint32_t i = lane; i < ncand; i += 32)
+          p.cand_pos[seg + i] = span_base + cands[i];
+      }
+    }
+    if (lane == 0) {
+      p.tile_first[span] = first;
+      p.tile_n[span] = ncand;
     }
     __syncwarp ();
   }

@@ -96,6 +96,33 @@ acm_qset_bucket (uint32_t key, uint32_t shift) {
   return (key * 0x9E3779B1u) >> shift; /* top bits of a multiplicative hash; buckets = 1 << (32 - shift) */
 }
 
+/* Stride-2 filter (byte alphabets, shortest keyword >= 4): only every second text position is tested, on a 3-byte window.
+ * A keyword ending at e contains the window ending at e and the one ending at e-1; exactly one of the two ends on a sampled
+ * position, so every keyword puts two 3-byte keys into the shared-memory filter: its last three bytes (role A: the keyword ends ON
+ * the sampled position s) and the three bytes before its last one (role B: it ends at s+1).
+ * The kernel builds the 32-bit filter key with one byte permute: the three window bytes in text order, the third one repeated. */
+ACM_HD uint32_t
+acm_s2_key (uint32_t b0, uint32_t b1, uint32_t b2) {
+  return b0 | (b1 << 8) | (b2 << 16) | (b2 << 24);
+}
+/* Second level, global memory (L2 resident): one 32-bit word per hashed 3-byte window; inside it two bits per (role, 4-byte
+ * window ending at the candidate end position).  One word load answers "may a keyword end at s?" and "... at s+1?". */
+#define ACM_PAIR_C0 0x9E3779B1u
+#define ACM_PAIR_CA 0x85EBCA77u
+#define ACM_PAIR_CB 0xC2B2AE3Du
+ACM_HD uint32_t
+acm_pair_word (uint32_t gram3 /* 24 bits, first byte lowest */, uint32_t log2_words) {
+  return (gram3 * ACM_PAIR_C0) >> (32 - log2_words);
+}
+ACM_HD uint32_t
+acm_pair_mask (uint32_t win4 /* the 4 bytes ending at the candidate end, last byte highest */, int role_b) {
+  const uint32_t h = win4 * (role_b ? ACM_PAIR_CB : ACM_PAIR_CA);
+  return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
+}
+#define ACM_S2_CAND_CAP 64u /* confirmed candidates a warp can hold per span */
+/* shared memory of one warp of the stride-2 kernel: staged hits (16-bit each) + the span's candidates */
+#define ACM_S2_WARP_BYTES(hit_cap) (16u + (hit_cap) * 2u + ACM_S2_CAND_CAP * 4u)
+
 typedef struct {
   uint32_t keyword;
   uint32_t length;
@@ -125,6 +152,12 @@ struct acm_tables {
   uint32_t *bloom2;           /* optional second level in global memory (0 when the first level is selective enough) */
   uint32_t bloom2_words;
   double bloom_fp;            /* expected false-positive rate of one probe, from the actual fill of every word */
+  uint32_t *bloom_s2;         /* stride-2 filter (width 1, shortest keyword >= 4): 3-byte keys, two per keyword; 0 when not applicable */
+  uint32_t bloom_s2_words, bloom_s2_k;
+  uint32_t s2_hit_cap;        /* raw filter hits a warp can stage per 2 KiB tile: 1.5 x the expected number + 32 */
+  double bloom_s2_hit_rate;   /* expected fraction of sampled positions that pass (false positives + true 3-byte windows) */
+  uint32_t *pairbits;         /* second level of the stride-2 filter, 1 << pairbits_log2 words */
+  uint32_t pairbits_log2;
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
   uint32_t *qset;             /* same keys as a compact set (4 keys per 16-byte bucket), widths 1 and 2 only */
@@ -144,7 +177,7 @@ extern "C" {
 #endif
 struct _ac_machine;
 /* Builds the images for the machine's current dictionary; returns 0 or an ACM_B200_ERR_* code. */
-int acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget);
+int acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget, uint64_t smem_optin);
 void acm_free_tables (struct acm_tables *t);
 /* Device symbol of the edge entering host state s (raw value or class id). */
 uint32_t acm_symbol_of_state (const struct _ac_machine *m, const struct _ac_state *s);

@@ -342,11 +342,12 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if width == 1 else "u32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "bytes_per_gpu": shard * width, "engine": st1["engine"], "nb_keywords": st1["nb_keywords"], "nb_states": st1["nb_states"],
                    "l2": "inputs larger than L2 (no flush needed)", "text_seed": hex(TEXT_SEED), "dict_seed": hex(DICT_SEED), "table_bytes": st1["table_bytes"],
-                   "smem_bytes": st1["smem_bytes"], "dictionary_build_s": round(build_s, 2), "finalise_ms": round(st1["finalise_ms"], 1)},
+                   "smem_bytes": st1["smem_bytes"], "dictionary_build_s": round(build_s, 2), "finalise_ms": round(st1["finalise_ms"], 1),
+                   "filter_stride": st1.get("filter_stride"), "filter_hit_rate": round(st1["filter_fp"], 5), "fallback_count": st1["fallback_count"]},
         "matches_per_s": total_matches / (ms_step * 1e-3), "matches_per_step": total_matches, "candidates_per_step_rank0": cands,
         "kernel_ms": {"main": float(np.mean(main_ms)), "all": float(np.mean(kernel_ms))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get(args.config), "peak_source": peak_src,
-                     "kernel": "filter_scan_kernel" if st1["engine"] == "filter" else "dfa_scan_kernel (count + emit passes)",
+                     "kernel": ("filter_scan_s2_kernel" if st1.get("filter_stride") == 2 else "filter_scan_kernel") if st1["engine"] == "filter" else "dfa_scan_kernel (count + emit passes)",
                      "algorithmic_bytes_per_launch": int(algo_bytes)},
         "clocks": clocks,
         "e2e": e2e,

@@ -62,7 +62,7 @@ def test_config3_random_patterns(engine):
     want = oracle_records(flat=flat, offsets=offsets, text=text, kind="port")
     got, st = gpu_scan(flat=flat, offsets=offsets, text=text, engine=engine)
     if engine == "auto":
-        assert st["engine"] == "filter" and st["fallback_count"] == 0
+        assert st["engine"] == "filter" and st["fallback_count"] == 0 and st["filter_stride"] == 2
     assert len(want) >= 2000 and np.array_equal(got, want), (engine, len(got), len(want))
 
 
@@ -259,3 +259,40 @@ def test_all_ones_and_zero_bytes(engine):
     want = oracle_records(words, text=text)
     got, st = gpu_scan(words, text=text, engine=engine)
     assert len(want) > 10_000 and np.array_equal(got, want), (engine, st["engine"], len(got), len(want))
+
+
+def test_stride2_kernel_tile_and_span_boundaries():
+    """Stride-2 filter kernel (byte alphabet, shortest keyword >= 4): keywords of both end parities and every length class planted
+    across the 2 KiB tile, 32 KiB span and text boundaries; with the kernel switched off the records must be the same."""
+    rng = np.random.default_rng(77)
+    kws = [rng.integers(0, 256, size=int(L), dtype=np.uint8).tobytes() for L in list(range(4, 12)) * 40 + [32, 31, 17] * 10]
+    n = 3 * 32768 + 2048 + 777
+    o = pyoracle.Oracle("port", 1)
+    o.insert_many(kws)
+    m = ac75().Machine(1)
+    m.insert_many(kws)
+    m.set_option("engine", "filter")
+    m1 = ac75().Machine(1)
+    m1.insert_many(kws)
+    m1.set_option("engine", "filter")
+    m1.set_option("stride2", 0)
+    total = 0
+    for delta in range(-8, 9):
+        text = rng.integers(0, 256, size=n, dtype=np.uint8)
+        for i, b in enumerate([4, 16, 512, 2048, 4096, 32768, 32768 + 2048, 65536, 3 * 32768, n]):
+            k = np.frombuffer(kws[(i * 17 + delta + 8) % len(kws)], dtype=np.uint8)
+            end = min(n, max(len(k), b + delta))  # one past the last byte of the planted keyword
+            text[end - len(k):end] = k
+        for lead in (0, 5, 2049):
+            want = o.scan(text, cap=1 << 20)
+            o.reset_cursor()
+            want = want[want["end"] >= lead]
+            got = m.scan(text, lead=lead, capacity=1 << 20)
+            got1 = m1.scan(text, lead=lead, capacity=1 << 20)
+            st, st1 = m.stats(), m1.stats()
+            assert st["filter_stride"] == 2 and st1["filter_stride"] == 1 and st["fallback_count"] == 0
+            assert np.array_equal(got, want), (delta, lead, len(got), len(want))
+            assert np.array_equal(got1, want), (delta, lead, len(got1), len(want))
+            total += len(want)
+    assert total > 300
+    m.close(), m1.close(), o.close()
