@@ -88,7 +88,7 @@ struct acm_device_image {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
   DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
@@ -101,6 +101,7 @@ struct acm_device_image {
   } *h_small = nullptr;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
   bool stride2 = false;   /* the stride-2 tables (bloom_s2, pairbits) are resident */
+  bool has_rpool = false; /* the reversed keyword pool (kw_meta, kw_rpool) is resident */
   ACMB200Stats stats = {};
 };
 
@@ -109,7 +110,7 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_text, &img->d_text2, &img->d_matches,
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
                      &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
@@ -195,10 +196,11 @@ finalise_locked (ACMachine *m, int device) {
         || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
         || (t.bloom_s2 && ((rc = upload (img->d_bloom_s2, t.bloom_s2, (size_t)t.bloom_s2_words * 4, st)) || (rc = upload (img->d_pairbits, t.pairbits, (size_t)4 << t.pairbits_log2, st))))
         || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
-        || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st)))
+        || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st))
+        || (t.kw_meta && ((rc = upload (img->d_kw_meta, t.kw_meta, ((size_t)t.nb_keywords + 1) * 8, st)) || (rc = upload (img->d_kw_rpool, t.kw_rpool, t.kw_rpool_words * 4, st)))))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot) + t.kw_pool_bytes + (uint64_t)t.nb_keywords * 12
-            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0) + (t.bloom_s2 ? (uint64_t)t.bloom_s2_words * 4 + ((uint64_t)4 << t.pairbits_log2) : 0);
+            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0) + (t.bloom_s2 ? (uint64_t)t.bloom_s2_words * 4 + ((uint64_t)4 << t.pairbits_log2) : 0) + (t.kw_meta ? (uint64_t)t.nb_keywords * 8 + t.kw_rpool_words * 4 : 0);
   } else {
     if ((rc = upload (img->d_delta, t.delta, t.delta_bytes, st)) || (rc = upload (img->d_out_offsets, t.out_offsets, ((size_t)t.nb_dfa_states - t.out_threshold + 1) * 4, st))
         || (rc = upload (img->d_out_entries, t.out_entries, t.nb_out_entries * sizeof (acm_output), st)))
@@ -221,6 +223,9 @@ finalise_locked (ACMachine *m, int device) {
   free (t.kw_len), t.kw_len = nullptr;
   free (t.kw_off), t.kw_off = nullptr;
   free (t.kw_pool), t.kw_pool = nullptr;
+  img->has_rpool = t.kw_meta != nullptr;
+  free (t.kw_meta), t.kw_meta = nullptr;
+  free (t.kw_rpool), t.kw_rpool = nullptr;
   free (t.edges), t.edges = nullptr;
   m->device_generation = m->generation;
   ACMB200Stats &s = img->stats;
@@ -437,6 +442,8 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.kw_len = img->d_kw_len.as<uint32_t> ();
     p.kw_off = img->d_kw_off.as<uint64_t> ();
     p.kw_pool = img->d_kw_pool.ptr;
+    p.kw_meta = img->has_rpool ? img->d_kw_meta.as<uint2> () : nullptr;
+    p.kw_rpool = img->d_kw_rpool.as<uint32_t> ();
     p.prefix = d_small->prefix;
     p.prefix_len = job.prefix_len;
     /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */

@@ -166,6 +166,8 @@ acm_free_tables (struct acm_tables *t) {
   free (t->kw_len);
   free (t->kw_off);
   free (t->kw_pool);
+  free (t->kw_meta);
+  free (t->kw_rpool);
   free (t->edges);
   memset (t, 0, sizeof (*t));
 }
@@ -347,6 +349,28 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
     pool_at += len;
   }
   t->nb_rev_nodes = nodes;
+  if (t->width == 1 && total_syms + 3ull * nk < 0xFFFFFFF0ull * 4) {
+    /* reversed, word-aligned copy of the pool: the tail compare of the verification kernels walks the text leftwards four bytes
+     * at a time against aligned 32-bit words */
+    uint64_t words = 0;
+    for (uint32_t r = 0; r < nk; r++)
+      words += (t->kw_len[r] + 3) / 4;
+    t->kw_meta = malloc (((size_t)nk + 1) * 2 * sizeof (uint32_t));
+    t->kw_rpool = calloc (words + 1, sizeof (uint32_t));
+    if (!t->kw_meta || !t->kw_rpool)
+      goto done;
+    t->kw_rpool_words = words + 1;
+    uint64_t at = 0;
+    for (uint32_t r = 0; r < nk; r++) {
+      const uint32_t len = t->kw_len[r];
+      const uint8_t *fwd = (const uint8_t *)t->kw_pool + t->kw_off[r];
+      t->kw_meta[2 * (size_t)r] = len;
+      t->kw_meta[2 * (size_t)r + 1] = (uint32_t)at;
+      for (uint32_t j = 0; j < len; j++)
+        t->kw_rpool[at + (j >> 2)] |= (uint32_t)fwd[len - 1 - j] << (8 * (j & 3));
+      at += (len + 3) / 4;
+    }
+  }
   /* keywords per subtree; children have larger ids than their parent */
   for (uint32_t v = nodes - 1; v >= 1; v--) {
     if (term_kw[v] != ACM_TAB_NONE) {

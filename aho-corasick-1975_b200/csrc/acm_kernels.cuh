@@ -401,6 +401,8 @@ struct FilterParams {
   const uint32_t *kw_len; /* tails: keyword id -> length, first symbol in the pool, the pool (forward symbols) */
   const uint64_t *kw_off;
   const void *kw_pool;
+  const uint2 *kw_meta;     /* width 1 (else null): keyword id -> {length, first word of its reversed bytes in kw_rpool} */
+  const uint32_t *kw_rpool;
   const uint32_t *prefix; /* symbols virtually preceding the text (carried cursor), prefix_len of them */
   uint32_t prefix_len;
   uint32_t stage_cap; /* raw hits a warp can stage per tile */
@@ -1165,12 +1167,35 @@ filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candid
     for (;;) {
       if (node != ACM_TAB_NONE && (node & ACM_TAIL_FLAG)) {
         /* exactly one keyword lies below: compare its remaining symbols with the text, right to left */
-        const uint32_t k = node & ~ACM_TAIL_FLAG, klen = p.kw_len[k];
-        const typename SymT<W>::type *kwsym = reinterpret_cast<const typename SymT<W>::type *> (p.kw_pool) + p.kw_off[k];
+        const uint32_t k = node & ~ACM_TAIL_FLAG;
+        uint32_t klen;
         bool same = true;
-        for (uint32_t j = len; j < klen && same; j++) {
-          uint32_t sym;
-          same = symbol_at<W> (p, pos - (int64_t)j, &sym) && sym == kwsym[klen - 1 - j];
+        if (W == 1 && p.kw_meta && (len & 3u) == 0 && (uint64_t)pos + 1 >= __ldg (&p.kw_meta[k]).x) {
+          /* the keyword lies inside the text: four bytes per step, aligned words of the text against the keyword's reversed,
+           * word-aligned copy.  Step i compares text bytes e-3..e (e = pos - len - 4i) with reversed-pool word len/4 + i. */
+          const uint2 meta = __ldg (&p.kw_meta[k]);
+          klen = meta.x;
+          const uint32_t *rp = p.kw_rpool + meta.y;
+          const uint32_t *tw = reinterpret_cast<const uint32_t *> (p.text);
+          if (len < klen) {
+            int64_t e = pos - (int64_t)len, wi = e >> 2;
+            const uint32_t sh = ((uint32_t)(e & 3) + 1u) * 8u;
+            uint32_t hi = tw[wi];
+            for (uint32_t j = len; j < klen && same; j += 4, wi--) {
+              const uint32_t lo = wi > 0 ? tw[wi - 1] : 0u;
+              const uint32_t t_rev = __byte_perm (__funnelshift_rc (lo, hi, sh), 0u, 0x0123); /* lowest byte = text byte e */
+              const uint32_t rem = klen - j, mask = rem >= 4 ? 0xFFFFFFFFu : (1u << (8 * rem)) - 1u;
+              same = ((t_rev ^ __ldg (rp + (j >> 2))) & mask) == 0;
+              hi = lo;
+            }
+          }
+        } else {
+          klen = p.kw_len[k];
+          const typename SymT<W>::type *kwsym = reinterpret_cast<const typename SymT<W>::type *> (p.kw_pool) + p.kw_off[k];
+          for (uint32_t j = len; j < klen && same; j++) {
+            uint32_t sym;
+            same = symbol_at<W> (p, pos - (int64_t)j, &sym) && sym == kwsym[klen - 1 - j];
+          }
         }
         if (same)
           report (k, klen);

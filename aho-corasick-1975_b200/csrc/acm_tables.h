@@ -170,6 +170,9 @@ struct acm_tables {
   uint64_t *kw_off;           /* keyword id -> first symbol in kw_pool */
   void *kw_pool;              /* every keyword's symbols, forward, `width` bytes each */
   uint64_t kw_pool_bytes;
+  uint32_t *kw_meta;          /* width 1: keyword id -> {length, first word in kw_rpool} (one 8-byte load) */
+  uint32_t *kw_rpool;         /* width 1: every keyword's bytes REVERSED, each keyword padded to whole 32-bit words */
+  uint64_t kw_rpool_words;
 };
 
 #ifdef __cplusplus
