@@ -102,6 +102,7 @@ struct acm_device_image {
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
   bool stride2 = false;   /* the stride-2 tables (bloom_s2, pairbits) are resident */
   bool has_rpool = false; /* the reversed keyword pool (kw_meta, kw_rpool) is resident */
+  bool prefer_dense = false; /* the last filter scan overflowed its candidate buffers: start the next one in dense mode */
   ACMB200Stats stats = {};
 };
 
@@ -214,6 +215,7 @@ finalise_locked (ACMachine *m, int device) {
   free (t.out_entries), t.out_entries = nullptr;
   free (t.bloom), t.bloom = nullptr;
   img->two_level = t.bloom2 != nullptr;
+  img->prefer_dense = false;
   free (t.bloom2), t.bloom2 = nullptr;
   img->stride2 = t.bloom_s2 != nullptr;
   free (t.bloom_s2), t.bloom_s2 = nullptr;
@@ -566,12 +568,16 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
   const uint64_t kDenseSegment = 64ull << 20; /* symbols */
   img->stats.last_nb_candidates = 0;
   ACMB200Match *used = nullptr;
-  int rc = run_filter_once<W> (m, img, job, false, user_matches, job.capacity, !matches_on_device, total, &used, true, true);
-  if (rc != kFilterOverflow) {
-    job.d_matches = used;
-    return rc;
+  int rc = kFilterOverflow;
+  if (!img->prefer_dense) {
+    rc = run_filter_once<W> (m, img, job, false, user_matches, job.capacity, !matches_on_device, total, &used, true, true);
+    if (rc != kFilterOverflow) {
+      job.d_matches = used;
+      return rc;
+    }
+    img->prefer_dense = true; /* texts this dense in candidates usually come in series: skip the doomed attempt next time */
+    img->stats.fallback_count++;
   }
-  img->stats.fallback_count++;
   img->stats.last_nb_candidates = 0;
   ACMB200Match *out = user_matches;
   if (!matches_on_device && job.capacity) {
@@ -599,6 +605,8 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
   }
   *total = grand;
   job.d_matches = out;
+  if (img->stats.last_nb_candidates < job.n / 64) /* sparse again: the next scan may use the fast mode */
+    img->prefer_dense = false;
   return ACM_B200_OK;
 }
 

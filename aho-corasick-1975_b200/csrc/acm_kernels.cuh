@@ -498,7 +498,7 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict
     if (kTwoLevel) { /* survivors of the shared-memory level ask the L2-resident level */
       uint32_t word2 = 0;
       if (t & 1u)
-        word2 = __ldg (bloom2 + __umulhi (folded * ACM_BLOOM_C3, nwords2));
+        word2 = __ldcg (bloom2 + __umulhi (folded * ACM_BLOOM_C3, nwords2)); /* L2 only: random table words must not evict text from L1 */
       const uint32_t h3 = __umulhi (folded, ACM_BLOOM_C4);
       t &= (word2 >> (h3 & 31u)) & (word2 >> ((h3 >> 5) & 31u));
     }
@@ -534,7 +534,7 @@ qset_contains (const FilterParams &p, uint32_t key) {
     return p.qset_has_empty_key != 0;
   const uint32_t mask = (1u << (32 - p.qset_shift)) - 1u;
   for (uint32_t b = acm_qset_bucket (key, p.qset_shift);; b = (b + 1) & mask) {
-    const uint4 c = __ldg (p.qset + b);
+    const uint4 c = __ldcg (p.qset + b); /* L2 only, as above */
     if (c.x == key || c.y == key || c.z == key || c.w == key)
       return true;
     if (c.x == ACM_QSET_EMPTY || c.y == ACM_QSET_EMPTY || c.z == ACM_QSET_EMPTY || c.w == ACM_QSET_EMPTY)

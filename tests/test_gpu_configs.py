@@ -152,4 +152,15 @@ def test_dense_fallback_runs_in_segments():
     w2 = want[want["end"] >= lead].copy()
     w2["end"] += 10**12
     assert np.array_equal(got2, w2)
+    # the second dense text went straight to the dense mode (no second doomed attempt) ...
+    assert m.stats()["fallback_count"] == 1
+    # ... and a sparse text afterwards is still scanned exactly, after which the fast mode is back
+    sparse = rng.integers(4, 256, size=1 << 20).astype(np.uint8)
+    k = flat[int(offsets[3]):int(offsets[4])]
+    sparse[5000:5000 + len(k)] = k
+    o.reset_cursor()
+    want3 = o.scan(sparse, cap=1 << 16)
+    for _ in range(2):
+        assert np.array_equal(m.scan(sparse, capacity=1 << 16), want3) and len(want3) >= 1
+    assert m.stats()["fallback_count"] == 1
     m.close(), o.close()
