@@ -928,6 +928,21 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         }
       }
 
+      if (!interior) { /* first / last tile: drop the tests on positions outside the text (zero padding: a thousand equal keys) or
+                          whose two candidate ends both lie before the first reportable one */
+#pragma unroll
+        for (int a = 0; a < kAcc; a++) {
+          uint32_t keep = 0;
+          for (int i = 0; i < 32 && a * 32 + i < 8 * kRows; i++) {
+            const uint32_t ti = a * 32 + i;
+            const uint64_t s = tile_base + (uint64_t)lane * 16 + (uint64_t)(ti >> 3) * 512 + (ti & 7u) * 2;
+            if (s < p.n && s + 1 >= first_end)
+              keep |= 0x80000000u >> i;
+          }
+          acc[a] &= keep >> kAccShift;
+        }
+      }
+
       /* ---- stage the hits as (lane << 6) | test index; slots from a warp scan of the per-lane counts (a shared counter would
        * serialise the ~28 lanes that have hits on one bank) ---- */
       uint32_t staged;

@@ -287,6 +287,8 @@ def main():
     barrier()
     clocks = sampler.stop(t_begin, time.time())
     st1 = m.stats()
+    print(f"[rank {rank}] ms/step(local)={ev0.elapsed_time(ev1) / max(args.steps, 1):.3f} kernel_ms={np.mean(kernel_ms):.3f} main_ms={np.mean(main_ms):.3f} "
+          f"fallbacks={st1['fallback_count']} stride={st1.get('filter_stride')} matches={local_matches} cands={cands}", file=sys.stderr)
     ms_step = ev0.elapsed_time(ev1) / max(args.steps, 1)
     if world > 1:
         t = torch.tensor([ms_step], dtype=torch.float64, device="cuda")

@@ -266,6 +266,7 @@ def test_stride2_kernel_tile_and_span_boundaries():
     across the 2 KiB tile, 32 KiB span and text boundaries; with the kernel switched off the records must be the same."""
     rng = np.random.default_rng(77)
     kws = [rng.integers(0, 256, size=int(L), dtype=np.uint8).tobytes() for L in list(range(4, 12)) * 40 + [32, 31, 17] * 10]
+    kws += [bytes(4), b"\x07" + bytes(5)]  # all-zero windows are keys: the zero padding of the last, partial tile must not count as hits
     n = 3 * 32768 + 2048 + 777
     o = pyoracle.Oracle("port", 1)
     o.insert_many(kws)
