@@ -81,7 +81,7 @@ typedef struct {
   uint64_t last_nb_symbols, last_nb_matches, last_nb_candidates;
   uint64_t main_kernel_launches, total_kernel_launches; /* since machine creation */
   uint64_t fallback_count;  /* scans re-run in the filter engine's dense mode because a candidate buffer overflowed */
-  double filter_fp;         /* expected false-positive rate of the shared-memory filter (0 for the DFA engines) */
+  double filter_fp;         /* expected pass rate of one test of the shared-memory filter on unrelated text (0 for the DFA engines) */
   uint64_t filter_stride;   /* last scan, filter engine: text positions per filter test (2 = the stride-2 kernel, 1 = every position; 0 = DFA) */
 } ACMB200Stats;
 
@@ -120,7 +120,9 @@ uint32_t acm_b200_max_keyword_length (const ACMachine *machine);
 int acm_b200_remap_text (ACMachine *machine, const void *letters, size_t letter_size, uint64_t nb, uint32_t *class_ids);
 
 /* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "bloom_words", "threads";
- * "stream_bytes" = size of the chunks host text is streamed in (default 256 MiB; host texts up to that size are copied whole). */
+ * "stream_bytes" = size of the chunks host text is streamed in (default 256 MiB; host texts up to that size are copied whole);
+ * "stride2" = 0 keeps the one-test-per-position filter kernel where the stride-2 kernel would apply (byte alphabet, shortest keyword
+ * >= 4 bytes); "s2_smem_kb" = shared-memory carve-out the stride-2 kernel is sized for (default 196: the rest of the SM stays L1). */
 int acm_b200_set_option (ACMachine *machine, const char *key, const char *value);
 int acm_b200_get_stats (ACMachine *machine, ACMB200Stats *stats);
 const char *acm_b200_last_error (void);
