@@ -89,14 +89,15 @@ struct acm_device_image {
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
   DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
-  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_small;
+  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_hot_spans, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
     uint32_t overflow;
     uint32_t pad;
     unsigned long long span_counter;
-    uint64_t pad2;
+    unsigned int hot_count; /* spans the stride-2 kernel left to filter_hot_spans_kernel */
+    uint32_t pad2;
     uint32_t prefix[1024];
   } *h_small = nullptr;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
@@ -112,7 +113,7 @@ acm_device_release (struct acm_device_image *img) {
     return;
   cudaSetDevice (img->device);
   for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
-                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_small })
+                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_hot_spans, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
     if (e)
@@ -429,6 +430,8 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.pairbits_log2 = t.pairbits_log2;
     p.span_counter = &d_small->span_counter;
     p.s2_hit_cap = t.s2_hit_cap;
+    p.hot_count = &d_small->hot_count;
+    p.hot_cap = s2 ? (uint32_t)std::max<uint64_t> (p.ntiles / 8, 64) : 0; /* more unfinished spans than that: the text is dense, use the dense mode */
     p.bloom = img->d_bloom.as<uint32_t> ();
     p.bloom_words = t.bloom_words;
     p.bloom_k = t.bloom_k;
@@ -463,7 +466,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
       return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
     int rc;
     if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = img->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
-        || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
+        || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_hot_spans.ensure ((size_t)p.hot_cap * 4 + 16)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
       return rc;
     p.cand_pos = img->d_cand_pos.as<uint64_t> ();
     p.cand_matches = img->d_cand_matches.as<uint32_t> ();
@@ -471,6 +474,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.cand_inline = img->d_cand_inline.as<uint4> ();
     p.tile_first = img->d_tile_first.as<uint64_t> ();
     p.tile_n = img->d_tile_n.as<uint32_t> ();
+    p.hot_spans = img->d_hot_spans.as<uint32_t> ();
     p.tile_matches = img->d_counts.as<uint32_t> ();
     p.tile_offsets = img->d_offsets.as<uint64_t> ();
     p.cand_count = &d_small->cand_count;
@@ -503,6 +507,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     img->h_small->grand_total = 0;
     img->h_small->overflow = 0;
     img->h_small->span_counter = 0;
+    img->h_small->hot_count = 0;
     CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
     const unsigned grid = (unsigned)std::min<uint64_t> (((s2 ? (job.n + 2047) / 2048 : p.ntiles) + warps - 1) / warps, (uint64_t)img->sm_count);
     if (first_segment)
@@ -520,6 +525,20 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
       if (dense)
         return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
       return kFilterOverflow;
+    }
+    if (s2 && img->h_small->hot_count) {
+      /* a few spans overflowed the stride-2 kernel's stages: they are redone exactly, everything else stands */
+      const uint32_t nb_hot = img->h_small->hot_count;
+      if (nb_hot > p.hot_cap)
+        return kFilterOverflow;
+      filter_hot_spans_kernel<<<(nb_hot + kHotWarps - 1) / kHotWarps, kHotWarps * 32, 0, job.st>>> (p, nb_hot);
+      CUDA_TRY (cudaGetLastError ());
+      CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
+      CUDA_TRY (cudaStreamSynchronize (job.st));
+      img->stats.total_kernel_launches += 1;
+      img->stats.hot_spans += nb_hot;
+      if (img->h_small->overflow)
+        return kFilterOverflow;
     }
     const uint64_t nb_cand = img->h_small->cand_count;
     const unsigned vgrid = (unsigned)((nb_cand + 255) / 256), tgrid = (unsigned)((p.ntiles + 255) / 256);

@@ -428,6 +428,9 @@ struct FilterParams {
   const uint32_t *pairbits;
   uint32_t pairbits_log2;
   uint32_t s2_hit_cap;
+  uint32_t *hot_spans;      /* spans F1s could not finish (a stage overflowed): redone exactly by filter_hot_spans_kernel */
+  uint32_t hot_cap;
+  unsigned int *hot_count;
   unsigned long long *span_counter;
 };
 
@@ -891,6 +894,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       break;
     const uint64_t tile0 = span * kSpanTiles, tile1 = min (ntiles, tile0 + kSpanTiles);
     uint32_t ncand = 0; /* warp-uniform: candidates of this span held in cands[], span-relative positions, ordered */
+    bool hot = false;   /* warp-uniform: a stage of this span overflowed, the span is left to filter_hot_spans_kernel */
     load_tile (tile0);
 
     for (uint64_t tile = tile0; tile < tile1; tile++) {
@@ -976,10 +980,9 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       if (tile + 1 < tile1)
         load_tile (tile + 1); /* in flight during the confirmation below */
       __syncwarp ();
-      if (staged > kHitCap) {
-        if (lane == 0)
-          atomicExch (p.overflow, 1u);
-        staged = kHitCap;
+      if (staged > kHitCap) { /* a run of equal bytes that happens to be a key, say: more hits than the stage holds */
+        hot = true;
+        staged = 0;
       }
 
       /* ends whose 4-byte window reaches into the carried-cursor prefix: kept unconditionally (F2 decides) */
@@ -1079,17 +1082,15 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       }
       __syncwarp ();
       if (ncand > ACM_S2_CAND_CAP) {
-        if (lane == 0)
-          atomicExch (p.overflow, 1u);
-        ncand = ACM_S2_CAND_CAP;
+        hot = true;
+        ncand = 0;
       }
       /* the tile's survivors were appended in staging order: sort them by position (rank = number of smaller ones) */
       const uint32_t fresh = ncand - tile_first_cand;
       if (fresh > 1) {
-        if (fresh > 32) {
-          if (lane == 0)
-            atomicExch (p.overflow, 1u);
-        } else {
+        if (fresh > 32)
+          hot = true;
+        else {
           const uint32_t mine_pos = (uint32_t)lane < fresh ? cands[tile_first_cand + lane] : 0xFFFFFFFFu;
           uint32_t rank = 0;
           for (uint32_t j = 0; j < fresh; j++)
@@ -1100,10 +1101,20 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           __syncwarp ();
         }
       }
+      if (hot)
+        break;
     }
 
     /* ---- one reservation per span ---- */
     uint64_t first = 0;
+    if (hot) { /* rare */
+      ncand = 0;
+      if (lane == 0) {
+        const unsigned int at = atomicAdd (p.hot_count, 1u);
+        if (at < p.hot_cap)
+          p.hot_spans[at] = (uint32_t)span;
+      }
+    }
     if (ncand) {
       unsigned long long seg = 0;
       if (lane == 0)
@@ -1125,6 +1136,62 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       p.tile_n[span] = ncand;
     }
     __syncwarp ();
+  }
+}
+
+/* F1h: the spans F1s left unfinished (more filter hits in a tile, or more candidates in the span, than its shared-memory stages
+ * hold).  One warp per such span tests EVERY end position of the span exactly (4-byte window in the q-gram key set, one L2 lookup
+ * per position), keeps the verdicts of the span as 1,024 ballot words in shared memory, reserves the span's segment of the candidate
+ * list once and writes the positions in order -- what F1s would have produced, without its capacity limits. */
+constexpr int kHotWarps = 4;
+__global__ void __launch_bounds__ (kHotWarps * 32)
+filter_hot_spans_kernel (const __grid_constant__ FilterParams p, uint32_t nb_hot) {
+  __shared__ uint32_t s_ballots[kHotWarps][kS2SpanBytes / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t h = blockIdx.x * kHotWarps + warp;
+  if (h >= nb_hot)
+    return;
+  const uint64_t span = p.hot_spans[h], span_base = span * kS2SpanBytes;
+  const uint64_t span_end = min (p.n, span_base + kS2SpanBytes);
+  const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
+  uint32_t *ballots = s_ballots[warp];
+  uint32_t total = 0;
+  for (uint32_t w = 0; w < kS2SpanBytes / 32; w++) {
+    const uint64_t e = span_base + (uint64_t)w * 32 + lane;
+    bool ok = false;
+    if (e < span_end && e >= p.lead) {
+      if (e >= 3) {
+        const uint32_t win4 = (uint32_t)text8[e - 3] | ((uint32_t)text8[e - 2] << 8) | ((uint32_t)text8[e - 1] << 16) | ((uint32_t)text8[e] << 24);
+        ok = qset_contains (p, win4);
+      } else
+        ok = p.prefix_len != 0; /* the window reaches into the carried-cursor prefix: F2 decides */
+    }
+    const uint32_t m = __ballot_sync (kFull, ok);
+    if (lane == 0)
+      ballots[w] = m;
+    total += __popc (m);
+  }
+  __syncwarp ();
+  unsigned long long seg = 0;
+  if (lane == 0 && total)
+    seg = atomicAdd (p.cand_count, (unsigned long long)total);
+  seg = __shfl_sync (kFull, seg, 0);
+  if (seg + total > p.cand_cap) {
+    if (lane == 0)
+      atomicExch (p.overflow, 1u);
+    total = 0;
+  }
+  uint64_t at = seg;
+  if (total)
+    for (uint32_t w = 0; w < kS2SpanBytes / 32; w++) {
+      const uint32_t m = ballots[w];
+      if (m >> lane & 1u)
+        p.cand_pos[at + __popc (m & ((1u << lane) - 1u))] = span_base + (uint64_t)w * 32 + lane;
+      at += __popc (m);
+    }
+  if (lane == 0) {
+    p.tile_first[span] = seg;
+    p.tile_n[span] = total;
   }
 }
 

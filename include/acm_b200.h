@@ -82,6 +82,7 @@ typedef struct {
   uint64_t main_kernel_launches, total_kernel_launches; /* since machine creation */
   uint64_t fallback_count;  /* scans re-run in the filter engine's dense mode because a candidate buffer overflowed */
   double filter_fp;         /* expected pass rate of one test of the shared-memory filter on unrelated text (0 for the DFA engines) */
+  uint64_t hot_spans;       /* 32 KiB spans the stride-2 kernel handed to the exact follow-up kernel because a stage overflowed (since creation) */
   uint64_t filter_stride;   /* last scan, filter engine: text positions per filter test (2 = the stride-2 kernel, 1 = every position; 0 = DFA) */
 } ACMB200Stats;
 

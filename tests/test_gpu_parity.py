@@ -297,3 +297,33 @@ def test_stride2_kernel_tile_and_span_boundaries():
             total += len(want)
     assert total > 300
     m.close(), m1.close(), o.close()
+
+
+def test_stride2_kernel_hot_spans_are_redone_exactly():
+    """A run of equal bytes whose 3-byte window is a filter key makes every test of several tiles hit; the stage holds ~100 hits.
+    Such spans are handed to the exact follow-up kernel (no whole-scan fallback) and the records still equal the oracle's."""
+    rng = np.random.default_rng(5)
+    kws = [rng.integers(0, 256, size=int(L), dtype=np.uint8).tobytes() for L in list(range(4, 20)) * 30]
+    kws += [b"\x01\x09\x09\x09", b"\x09\x09\x09\x02\x03"]  # (9,9,9) is a key of both roles; a run of 9s matches neither keyword
+    text = rng.integers(0, 256, size=200_000, dtype=np.uint8)
+    text[50_000:57_000] = 9
+    text[57_000:57_002] = (2, 3)  # ... until the run ends in the second keyword
+    text[120_001:123_500] = 9
+    want = oracle_records(kws, text=text, kind="port")
+    m = ac75().Machine(1)
+    m.insert_many(kws)
+    m.set_option("engine", "filter")
+    got = m.scan(text, capacity=1 << 16)
+    st = m.stats()
+    assert st["filter_stride"] == 2 and st["fallback_count"] == 0 and 2 <= st["hot_spans"] <= 4, st
+    assert len(want) >= 1 and np.array_equal(got, want), (len(got), len(want))
+    # a span with more true candidates than the warp's candidate buffer holds (a keyword planted every 64 bytes) takes the same route
+    text2 = rng.integers(0, 256, size=200_000, dtype=np.uint8)
+    k = np.frombuffer(kws[3], dtype=np.uint8)
+    for at in range(70_000, 80_000, 64):
+        text2[at:at + len(k)] = k
+    want2 = oracle_records(kws, text=text2, kind="port")
+    got2 = m.scan(text2, capacity=1 << 16)
+    assert m.stats()["fallback_count"] == 0 and m.stats()["hot_spans"] > st["hot_spans"]
+    assert len(want2) >= 150 and np.array_equal(got2, want2), (len(got2), len(want2))
+    m.close()
