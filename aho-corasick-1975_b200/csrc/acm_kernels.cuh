@@ -963,6 +963,13 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
             incl += o;
         }
         staged = __shfl_sync (kFull, incl, 31);
+        if (staged > kHitCap) { /* a run of equal bytes that happens to be a key, say: more hits than the stage holds */
+          hot = true;
+          staged = 0;
+#pragma unroll
+          for (int a = 0; a < kAcc; a++)
+            acc[a] = 0;
+        }
         uint32_t at = incl - cnt;
 #pragma unroll
         for (int a = 0; a < kAcc; a++) {
@@ -971,19 +978,13 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           while (bits) {
             const uint32_t ti = __clz (bits);
             bits &= ~(0x80000000u >> ti);
-            if (at < kHitCap)
-              hits[at] = (uint16_t)(tag | ti);
-            at++;
+            hits[at++] = (uint16_t)(tag | ti);
           }
         }
       }
       if (tile + 1 < tile1)
         load_tile (tile + 1); /* in flight during the confirmation below */
       __syncwarp ();
-      if (staged > kHitCap) { /* a run of equal bytes that happens to be a key, say: more hits than the stage holds */
-        hot = true;
-        staged = 0;
-      }
 
       /* ends whose 4-byte window reaches into the carried-cursor prefix: kept unconditionally (F2 decides) */
       if (tile == 0 && p.prefix_len) {
