@@ -874,11 +874,16 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         if (byte0 + 16 <= p.n)
           v[r] = *reinterpret_cast<const uint4 *> (text8 + byte0);
         else {
-          uint32_t w[4] = { 0, 0, 0, 0 };
-          for (int i = 0; i < 16; i++)
-            if (byte0 + i < p.n)
-              w[i >> 2] |= (uint32_t)text8[byte0 + i] << (8 * (i & 3));
-          v[r] = make_uint4 (w[0], w[1], w[2], w[3]);
+          uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0; /* not unrolled: this path runs for one or two tiles per scan */
+#pragma unroll 1
+          for (int i = 15; i >= 0; i--) {
+            const uint32_t b = byte0 + i < p.n ? text8[byte0 + i] : 0u;
+            w3 = (w3 << 8) | (w2 >> 24);
+            w2 = (w2 << 8) | (w1 >> 24);
+            w1 = (w1 << 8) | (w0 >> 24);
+            w0 = (w0 << 8) | b;
+          }
+          v[r] = make_uint4 (w0, w1, w2, w3);
         }
       }
       before_tile = base >= 4 ? *reinterpret_cast<const uint32_t *> (ptr - 4) : 0;
