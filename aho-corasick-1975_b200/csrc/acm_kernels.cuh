@@ -198,14 +198,27 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
           count += hi - lo;
       }
     };
-    /* warm-up + chunk, 16 bytes at a time while a whole vector is inside the text */
-    while (pos + 16 <= end) {
-      const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
+    /* warm-up + chunk, 16 bytes at a time while a whole vector is inside the text.  A thread's loads are a dependent chain of
+     * DRAM round trips (nothing else of its chunk is in flight), so the next vector is requested before the current one is walked
+     * and the line after that is pulled into L2. */
+    bool have = pos + 16 <= end;
+    uint4 nxt = make_uint4 (0, 0, 0, 0);
+    if (have)
+      nxt = *reinterpret_cast<const uint4 *> (p.text + pos);
+    while (have) {
+      const uint4 v = nxt;
+      const uint64_t at0 = pos;
+      pos += 16;
+      have = pos + 16 <= end;
+      if (have) {
+        nxt = *reinterpret_cast<const uint4 *> (p.text + pos);
+        if ((pos & 127) == 0 && pos + 256 <= end)
+          asm volatile ("prefetch.global.L2 [%0];" ::"l"(p.text + pos + 128));
+      }
       const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
       for (int i = 0; i < 16; i++)
-        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, pos + i);
-      pos += 16;
+        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, at0 + i);
     }
     for (; pos < end; pos++)
       step (p.text[pos], pos);
@@ -313,13 +326,21 @@ dfa_emit_kernel (const __grid_constant__ DfaParams p) {
 
     auto drain = [&] (uint32_t count) { queued = emit_drain (ws, p, thr, warp_origin, queued, count); };
 
+    /* the next vector of the lane's chunk is requested one round ahead (see dfa_scan_kernel) */
+    uint4 nxt = make_uint4 (0, 0, 0, 0);
+    if (pos + 16 <= end)
+      nxt = *reinterpret_cast<const uint4 *> (p.text + pos);
     while (__any_sync (kFull, pos < end)) {
       /* next 16 bytes of this lane's walk (fewer at the end of its chunk) */
       uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, nvalid = 0;
       if (pos + 16 <= end) {
-        const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
-        w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        w0 = nxt.x, w1 = nxt.y, w2 = nxt.z, w3 = nxt.w;
         nvalid = 16;
+        if (pos + 32 <= end) {
+          nxt = *reinterpret_cast<const uint4 *> (p.text + pos + 16);
+          if (((pos + 16) & 127) == 0 && pos + 272 <= end)
+            asm volatile ("prefetch.global.L2 [%0];" ::"l"(p.text + pos + 144));
+        }
       } else if (pos < end) {
         nvalid = (uint32_t)(end - pos);
 #pragma unroll
