@@ -201,25 +201,42 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     /* warm-up + chunk, 16 bytes at a time while a whole vector is inside the text.  A thread's loads are a dependent chain of
      * DRAM round trips (nothing else of its chunk is in flight), so the next vector is requested before the current one is walked
      * and the line after that is pulled into L2. */
-    bool have = pos + 16 <= end;
-    uint4 nxt = make_uint4 (0, 0, 0, 0);
-    if (have)
-      nxt = *reinterpret_cast<const uint4 *> (p.text + pos);
-    while (have) {
-      const uint4 v = nxt;
-      const uint64_t at0 = pos;
-      pos += 16;
-      have = pos + 16 <= end;
-      if (have) {
-        nxt = *reinterpret_cast<const uint4 *> (p.text + pos);
-        if ((pos & 127) == 0 && pos + 256 <= end)
-          asm volatile ("prefetch.global.L2 [%0];" ::"l"(p.text + pos + 128));
-      }
+    /* 32 bytes (one sector) per round while two whole vectors are inside the text, the next round's pair requested before this
+     * round is walked; then at most one single vector */
+    auto round16 = [&] () {
+      const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
       const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
       for (int i = 0; i < 16; i++)
+        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, pos + i);
+      pos += 16;
+    };
+    if ((pos & 31) && pos + 16 <= end)
+      round16 (); /* chunks start on 16-byte boundaries: get onto a sector boundary */
+    bool have = pos + 32 <= end;
+    uint4 na = make_uint4 (0, 0, 0, 0), nb = na;
+    if (have) {
+      na = *reinterpret_cast<const uint4 *> (p.text + pos);
+      nb = *reinterpret_cast<const uint4 *> (p.text + pos + 16);
+    }
+    while (have) {
+      const uint4 va = na, vb = nb;
+      const uint64_t at0 = pos;
+      pos += 32;
+      have = pos + 32 <= end;
+      if (have) {
+        na = *reinterpret_cast<const uint4 *> (p.text + pos);
+        nb = *reinterpret_cast<const uint4 *> (p.text + pos + 16);
+        if ((pos & 127) == 0 && pos + 256 <= end)
+          asm volatile ("prefetch.global.L2 [%0];" ::"l"(p.text + pos + 128));
+      }
+      const uint32_t w[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
+#pragma unroll
+      for (int i = 0; i < 32; i++)
         step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, at0 + i);
     }
+    while (pos + 16 <= end)
+      round16 ();
     for (; pos < end; pos++)
       step (p.text[pos], pos);
     if (!kEmit)
