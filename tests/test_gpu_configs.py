@@ -125,6 +125,13 @@ def test_config3_full_size_properties():
         k = m.scan_device(d_text.data_ptr() + a - lead, bnd - a + lead, lead=lead, base=a - lead, d_matches_ptr=d_out.data_ptr(), capacity=cap)
         parts.append(d_out[: k * 16].cpu().numpy().view(ac75().MATCH_DTYPE).copy())
     assert sum(len(p) for p in parts) == total and np.array_equal(np.concatenate(parts), recs)
+    # (5) the two filter kernels are independent implementations of the same first stage: at the full size the stride-2 kernel
+    # (used above) and the one-test-per-position kernel must produce the same records, byte for byte
+    assert m.stats()["filter_stride"] == 2
+    m.set_option("stride2", 0)
+    total1 = m.scan_device(d_text.data_ptr(), n, d_matches_ptr=d_out.data_ptr(), capacity=cap)
+    assert m.stats()["filter_stride"] == 1 and total1 == total
+    assert np.array_equal(d_out[: total1 * 16].cpu().numpy().view(ac75().MATCH_DTYPE), recs)
     m.close(), o.close()
 
 
