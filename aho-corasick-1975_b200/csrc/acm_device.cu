@@ -89,7 +89,7 @@ struct acm_device_image {
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
   DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
-  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_hot_spans, d_small;
+  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_hot_spans, d_events, d_chunk_events, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
@@ -113,7 +113,7 @@ acm_device_release (struct acm_device_image *img) {
     return;
   cudaSetDevice (img->device);
   for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
-                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_hot_spans, &img->d_small })
+                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_hot_spans, &img->d_events, &img->d_chunk_events, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
     if (e)
@@ -274,6 +274,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_stream_bytes = strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_smem_kb"))
     m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++;
+  else if (!strcmp (key, "dfa_events")) /* 0: pass 2 of the DFA engines always walks the text again */
+    m->option_no_events = !strtoull (value, 0, 10);
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
     m->option_no_stride2 = !strtoull (value, 0, 10), m->generation++;
   else
@@ -350,6 +352,8 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   uint64_t want_threads = m->option_threads ? m->option_threads : (uint64_t)img->sm_count * blocks_per_sm * threads;
   const uint64_t min_chunk = std::max<uint64_t> (256, (uint64_t)(4 * p.warm + 15) / 16 * 16);
   p.chunk = std::max<uint64_t> (min_chunk, ((job.n + want_threads - 1) / want_threads + 15) / 16 * 16);
+  if (kShared && sizeof (Entry) == 2 && !m->option_threads)
+    p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 32768)); /* positions inside a chunk fit 16 bits (pass 1 events); huge texts: several chunks per thread */
   p.nchunks = (job.n + p.chunk - 1) / p.chunk;
   const unsigned grid = (unsigned)std::min<uint64_t> ((p.nchunks + threads - 1) / threads, (uint64_t)img->sm_count * blocks_per_sm);
 
@@ -360,10 +364,27 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   p.chunk_offsets = img->d_offsets.as<uint64_t> ();
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
 
-  auto count_k = dfa_scan_kernel<Entry, kShared, false>;
+  /* pass 1 records its events when it can (shared-memory engine: 16-bit output-state index; chunk offsets of 16 bits; one event
+   * slot per 4 symbols, i.e. as many bytes as the text): pass 2 then expands them instead of walking the text again */
+  bool use_events = kShared && sizeof (Entry) == 2 && p.chunk <= 65536 && p.nb_out_states <= 65536 && !m->option_no_events;
+  if (use_events) {
+    p.events_per_chunk = (uint32_t)(p.chunk / 4);
+    if (img->d_events.ensure (p.nchunks * p.events_per_chunk * 4) || img->d_chunk_events.ensure (p.nchunks * 4)) {
+      use_events = false; /* no room: walk twice */
+      g_error[0] = 0;
+    }
+  }
+  if (use_events) {
+    p.events = img->d_events.as<uint32_t> ();
+    p.chunk_events = img->d_chunk_events.as<uint32_t> ();
+    p.events_overflow = &img->d_small.as<acm_device_image::Small> ()->overflow;
+    img->h_small->overflow = 0;
+    CUDA_TRY (cudaMemcpyAsync (&img->d_small.as<acm_device_image::Small> ()->overflow, &img->h_small->overflow, 4, cudaMemcpyHostToDevice, job.st));
+  }
+  void (*count_k) (const DfaParams) = use_events ? dfa_scan_kernel<Entry, kShared, false, true> : dfa_scan_kernel<Entry, kShared, false, false>;
   /* pass 2: warp-cooperative emit when positions relative to a warp's 32 chunks fit 32 bits (always, short of absurd chunk sizes) */
   const bool coop = p.chunk * 32 < (1ull << 32);
-  auto emit_k = coop ? dfa_emit_kernel<Entry, kShared> : dfa_scan_kernel<Entry, kShared, true>;
+  void (*emit_k) (const DfaParams) = coop ? dfa_emit_kernel<Entry, kShared> : dfa_scan_kernel<Entry, kShared, true, false>;
   const size_t emit_smem = smem + (coop ? sizeof (EmitWarpState) * (threads / 32) : 0);
   CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)count_smem));
   CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
@@ -376,10 +397,14 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   if ((rc = device_exclusive_scan (img, p.chunk_counts, p.nchunks, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
     return rc;
   CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
+  if (use_events)
+    CUDA_TRY (cudaMemcpyAsync (&img->h_small->overflow, &d_small->overflow, 4, cudaMemcpyDeviceToHost, job.st));
   CUDA_TRY (cudaStreamSynchronize (job.st));
   *total = img->h_small->grand_total;
   img->stats.main_kernel_launches += 1;
   img->stats.total_kernel_launches += 1;
+  if (use_events && img->h_small->overflow)
+    use_events = false; /* a chunk met more output states than it has event slots: pass 2 walks */
 
   const uint64_t want = std::min<uint64_t> (*total, job.capacity);
   CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
@@ -392,7 +417,12 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
       p.matches = img->d_matches.as<ACMB200Match> ();
     }
     p.capacity = want;
-    emit_k<<<grid, threads, emit_smem, job.st>>> (p);
+    if (use_events)
+      img->stats.dfa_event_scans++;
+    if (use_events)
+      dfa_emit_events_kernel<<<(unsigned)std::min<uint64_t> ((p.nchunks + 7) / 8, (uint64_t)img->sm_count * 16), 256, 0, job.st>>> (p);
+    else
+      emit_k<<<grid, threads, emit_smem, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
     img->stats.main_kernel_launches += 1;
     img->stats.total_kernel_launches += 1;

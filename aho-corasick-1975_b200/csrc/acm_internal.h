@@ -87,7 +87,7 @@ struct _ac_machine {
   uint64_t device_generation;
   char engine_override[16];
   uint64_t option_bloom_words, option_threads, option_stream_bytes;
-  int option_no_stride2;
+  int option_no_stride2, option_no_events;
   uint64_t option_s2_smem_kb;
 };
 

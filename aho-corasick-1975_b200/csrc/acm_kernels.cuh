@@ -139,10 +139,16 @@ struct DfaParams {
   const uint64_t *chunk_offsets; /* pass 2 in */
   ACMB200Match *matches;
   uint64_t capacity;
+  /* pass 1 can record WHERE it met an output state (position inside the chunk | output state << 16), so that pass 2 expands the
+   * recorded events instead of walking the text a second time (shared-memory engine, chunks of at most 65,536 symbols) */
+  uint32_t *events;         /* [nchunks][events_per_chunk] */
+  uint32_t *chunk_events;   /* [nchunks] events met (may exceed events_per_chunk: then *events_overflow is set and pass 2 walks) */
+  uint32_t events_per_chunk;
+  uint32_t *events_overflow;
   uint8_t class_of_byte[256];
 };
 
-template <typename Entry, bool kShared, bool kEmit>
+template <typename Entry, bool kShared, bool kEmit, bool kEvents = false>
 __global__ void __launch_bounds__ (kShared ? 1024 : 256, kShared ? 1 : 2)
 dfa_scan_kernel (const __grid_constant__ DfaParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
@@ -176,13 +182,19 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     const bool from_origin = start <= p.warm;
     uint32_t state = from_origin ? p.init_state : 0;
     uint64_t pos = from_origin ? 0 : (start - p.warm) & ~(uint64_t)15;
-    uint32_t count = 0;
+    uint32_t count = 0, nev = 0;
     uint64_t out = kEmit ? p.chunk_offsets[c] : 0;
+    uint32_t *my_events = kEvents ? p.events + c * p.events_per_chunk : nullptr;
 
     auto step = [&] (uint32_t byte, uint64_t at) {
       state = delta[state * K + s_class[byte]];
       if (state >= thr && at >= report_from) {
         const uint32_t o = state - thr;
+        if (kEvents) {
+          if (nev < p.events_per_chunk)
+            my_events[nev] = (uint32_t)(at - start) | (o << 16);
+          nev++;
+        }
         if (smem_counts) {
           count += s_counts[o];
           return;
@@ -241,6 +253,52 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
       step (p.text[pos], pos);
     if (!kEmit)
       p.chunk_counts[c] = count;
+    if (kEvents) {
+      p.chunk_events[c] = nev;
+      if (nev > p.events_per_chunk)
+        atomicExch (p.events_overflow, 1u);
+    }
+  }
+}
+
+/* Pass 2 of the shared-memory DFA engine when pass 1 recorded its events: no walk, no table.  A warp takes one chunk at a time and
+ * expands 32 of its events per step: records per event from the CSR offsets, a warp scan for the positions, and stores that are
+ * contiguous across the warp (the records of a chunk are contiguous in the output, in position order, longest keyword first). */
+__global__ void __launch_bounds__ (256)
+dfa_emit_events_kernel (const __grid_constant__ DfaParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t c = warp_global; c < p.nchunks; c += nwarps) {
+    const uint32_t nev = p.chunk_events[c];
+    if (!nev)
+      continue;
+    const uint32_t *ev = p.events + c * p.events_per_chunk;
+    const uint64_t chunk_start = c * p.chunk;
+    uint64_t out = p.chunk_offsets[c];
+    for (uint32_t i0 = 0; i0 < nev; i0 += 32) {
+      uint32_t lo = 0, n = 0, rel = 0;
+      if (i0 + lane < nev) {
+        const uint32_t e = ev[i0 + lane], o = e >> 16;
+        rel = e & 0xFFFFu;
+        lo = p.out_offsets[o];
+        n = p.out_offsets[o + 1] - lo;
+      }
+      uint32_t incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync (kFull, incl, d);
+        if (lane >= d)
+          incl += v;
+      }
+      const uint32_t total = __shfl_sync (kFull, incl, 31);
+      uint64_t at = out + (incl - n);
+      for (uint32_t j = 0; j < n; j++, at++)
+        if (at < p.capacity) {
+          const acm_output e = p.out_entries[lo + j];
+          p.matches[at] = ACMB200Match{ p.base + chunk_start + rel, e.keyword, e.length };
+        }
+      out += total;
+    }
   }
 }
 

@@ -83,6 +83,7 @@ typedef struct {
   uint64_t fallback_count;  /* scans re-run in the filter engine's dense mode because a candidate buffer overflowed */
   double filter_fp;         /* expected pass rate of one test of the shared-memory filter on unrelated text (0 for the DFA engines) */
   uint64_t hot_spans;       /* 32 KiB spans the stride-2 kernel handed to the exact follow-up kernel because a stage overflowed (since creation) */
+  uint64_t dfa_event_scans; /* DFA engines: scans whose second pass expanded the events recorded by the first instead of walking the text again */
   uint64_t filter_stride;   /* last scan, filter engine: text positions per filter test (2 = the stride-2 kernel, 1 = every position; 0 = DFA) */
 } ACMB200Stats;
 
@@ -122,6 +123,7 @@ int acm_b200_remap_text (ACMachine *machine, const void *letters, size_t letter_
 
 /* Tuning / test knobs: "engine" = auto|dfa_smem|dfa_global|filter ; "bloom_words", "threads";
  * "stream_bytes" = size of the chunks host text is streamed in (default 256 MiB; host texts up to that size are copied whole);
+ * "dfa_events" = 0 makes the second pass of the DFA engines walk the text again instead of expanding recorded events;
  * "stride2" = 0 keeps the one-test-per-position filter kernel where the stride-2 kernel would apply (byte alphabet, shortest keyword
  * >= 4 bytes); "s2_smem_kb" = shared-memory carve-out the stride-2 kernel is sized for (default 196: the rest of the SM stays L1). */
 int acm_b200_set_option (ACMachine *machine, const char *key, const char *value);

@@ -327,3 +327,36 @@ def test_stride2_kernel_hot_spans_are_redone_exactly():
     assert m.stats()["fallback_count"] == 0 and m.stats()["hot_spans"] > st["hot_spans"]
     assert len(want2) >= 150 and np.array_equal(got2, want2), (len(got2), len(want2))
     m.close()
+
+
+def test_dfa_second_pass_from_recorded_events(novel):
+    """Shared-memory DFA engine: pass 1 records where it met an output state and pass 2 expands those events; with the recording
+    switched off pass 2 walks the text again.  Both must give the oracle's records; a text with more events than slots (one event
+    slot per 4 symbols) must fall back to the walk by itself."""
+    words = config2_keywords(novel, 300)
+    flat, offsets = pack(words)
+    text = ac75().generate_text(3 << 20, kind=1, plant_period=512, dict_flat=flat, dict_offsets=offsets)
+    want = oracle_records(words, text=text, kind="port")
+    for events in (1, 0):
+        m = ac75().Machine(1)
+        m.insert_many(words)
+        m.set_option("engine", "dfa_smem")
+        m.set_option("dfa_events", events)
+        got = m.scan(text, capacity=1 << 22)
+        lead_got = m.scan(text, lead=100_001, base=7, capacity=1 << 22)
+        st = m.stats()
+        assert st["engine"] == "dfa_smem" and st["dfa_event_scans"] == (2 if events else 0), st
+        assert len(want) > 100_000 and np.array_equal(got, want)
+        w2 = want[want["end"] >= 100_001].copy()
+        w2["end"] += 7
+        assert np.array_equal(lead_got, w2)
+        m.close()
+    # every symbol ends a keyword: more events than slots, the second pass walks
+    m = ac75().Machine(1)
+    m.insert_many([b"a", b"aa", b"ab"])
+    m.set_option("engine", "dfa_smem")
+    dense = np.frombuffer(b"aab" * 50_000, dtype=np.uint8)
+    want = oracle_records([b"a", b"aa", b"ab"], text=dense, kind="port")
+    got = m.scan(dense, capacity=1 << 20)
+    assert m.stats()["dfa_event_scans"] == 0 and np.array_equal(got, want) and len(want) > 150_000
+    m.close()
