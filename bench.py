@@ -349,7 +349,7 @@ def main():
         "matches_per_s": total_matches / (ms_step * 1e-3), "matches_per_step": total_matches, "candidates_per_step_rank0": cands,
         "kernel_ms": {"main": float(np.mean(main_ms)), "all": float(np.mean(kernel_ms))},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": prof.get(args.config), "peak_source": peak_src,
-                     "kernel": ("filter_scan_s2_kernel" if st1.get("filter_stride") == 2 else "filter_scan_kernel") if st1["engine"] == "filter" else "dfa_scan_kernel (count + emit passes)",
+                     "kernel": ("filter_scan_s2_kernel" if st1.get("filter_stride") == 2 else "filter_scan_kernel") if st1["engine"] == "filter" else "dfa_scan_kernel (count + event recording) + dfa_emit_events_kernel" if st1.get("dfa_event_scans") else "dfa_scan_kernel (count) + dfa_emit_kernel (walking emit)",
                      "algorithmic_bytes_per_launch": int(algo_bytes)},
         "clocks": clocks,
         "e2e": e2e,
