@@ -352,6 +352,7 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   uint64_t want_threads = m->option_threads ? m->option_threads : (uint64_t)img->sm_count * blocks_per_sm * threads;
   const uint64_t min_chunk = std::max<uint64_t> (256, (uint64_t)(4 * p.warm + 15) / 16 * 16);
   p.chunk = std::max<uint64_t> (min_chunk, ((job.n + want_threads - 1) / want_threads + 15) / 16 * 16);
+  p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 1ull << 30)); /* the kernels keep chunk-relative positions in 32 bits */
   if (kShared && sizeof (Entry) == 2 && !m->option_threads)
     p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 32768)); /* positions inside a chunk fit 16 bits (pass 1 events); huge texts: several chunks per thread */
   p.nchunks = (job.n + p.chunk - 1) / p.chunk;

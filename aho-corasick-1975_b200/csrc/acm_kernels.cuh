@@ -186,13 +186,17 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     uint64_t out = kEmit ? p.chunk_offsets[c] : 0;
     uint32_t *my_events = kEvents ? p.events + c * p.events_per_chunk : nullptr;
 
-    auto step = [&] (uint32_t byte, uint64_t at) {
+    /* positions are walked relative to the chunk start, in 32 bits (negative during the warm-up): the per-byte test is one
+     * compare, and the recorded event needs no 64-bit arithmetic */
+    const int32_t report_rel = (int32_t)(report_from - start);
+    auto step = [&] (uint32_t byte, int32_t rel) {
       state = delta[state * K + s_class[byte]];
-      if (state >= thr && at >= report_from) {
+      if (state >= thr && rel >= report_rel) {
         const uint32_t o = state - thr;
+        const uint64_t at = start + (int64_t)rel; /* only the emitting variant uses it */
         if (kEvents) {
           if (nev < p.events_per_chunk)
-            my_events[nev] = (uint32_t)(at - start) | (o << 16);
+            my_events[nev] = (uint32_t)rel | (o << 16);
           nev++;
         }
         if (smem_counts) {
@@ -218,9 +222,10 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     auto round16 = [&] () {
       const uint4 v = *reinterpret_cast<const uint4 *> (p.text + pos);
       const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+      const int32_t rel0 = (int32_t)((int64_t)pos - (int64_t)start);
 #pragma unroll
       for (int i = 0; i < 16; i++)
-        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, pos + i);
+        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, rel0 + i);
       pos += 16;
     };
     if ((pos & 31) && pos + 16 <= end)
@@ -233,7 +238,7 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
     }
     while (have) {
       const uint4 va = na, vb = nb;
-      const uint64_t at0 = pos;
+      const int32_t rel0 = (int32_t)((int64_t)pos - (int64_t)start);
       pos += 32;
       have = pos + 32 <= end;
       if (have) {
@@ -245,12 +250,12 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
       const uint32_t w[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
 #pragma unroll
       for (int i = 0; i < 32; i++)
-        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, at0 + i);
+        step ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu, rel0 + i);
     }
     while (pos + 16 <= end)
       round16 ();
     for (; pos < end; pos++)
-      step (p.text[pos], pos);
+      step (p.text[pos], (int32_t)((int64_t)pos - (int64_t)start));
     if (!kEmit)
       p.chunk_counts[c] = count;
     if (kEvents) {
