@@ -4,16 +4,20 @@
  *
  *  DFA engines (byte alphabets).  The text is cut into per-thread chunks; every thread first re-reads the
  *  (max keyword length - 1) symbols before its chunk from state 0 and then walks its chunk through the dense delta table
- *  (one class lookup + one delta lookup per byte).  Pass 1 counts the occurrences of every chunk, a device scan turns the
- *  counts into offsets, pass 2 re-walks and writes the records in place -- so the output is in the reference's emission order
- *  without any sort.  delta lives in shared memory (uint16 entries) or in global memory (uint32 entries, L2 resident).
+ *  (one class lookup + one delta lookup per byte).  Pass 1 counts the occurrences of every chunk -- and, in the shared-memory
+ *  engine, records where it met an output state -- a device scan turns the counts into offsets, pass 2 expands the recorded
+ *  events chunk by chunk (dfa_emit_events_kernel) or, where nothing was recorded, re-walks and writes the records in place
+ *  (dfa_emit_kernel) -- so the output is in the reference's emission order without any sort.  delta lives in shared memory
+ *  (uint16 entries) or in global memory (uint32 entries, L2 resident).
  *
  *  Filter engine (any alphabet).  A keyword can only END at position p if the q symbols ending at p are the last q symbols
  *  of some keyword (q = min(shortest keyword, 4 bytes / 2 wider symbols)).  Kernel F1 streams the text with coalesced 16-byte
  *  loads, tests every position against a blocked Bloom filter in shared memory (one 32-bit shared load per position), confirms
  *  the survivors in an exact q-gram hash table (L2) and appends the confirmed positions of each warp tile, in position order,
- *  to a candidate list (ballot/popc compaction).  F2 walks the reverse trie leftwards from every candidate and counts, a device
- *  scan gives offsets, F4 walks again and writes the records, longest keyword first.
+ *  to a candidate list (ballot/popc compaction).  For byte dictionaries whose shortest keyword has at least 4 bytes, F1s does
+ *  the same with one shared load per TWO positions (3-byte windows on every second position, a pair table in L2 as second
+ *  level) and F1h redoes exactly the few 32 KiB spans whose stages overflowed.  F2 walks the reverse trie leftwards from every
+ *  candidate and counts, a device scan gives offsets, F4 walks again and writes the records, longest keyword first.
  */
 #pragma once
 #include "acm_tables.h"
