@@ -200,7 +200,8 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
         const uint64_t at = start + (int64_t)rel; /* only the emitting variant uses it */
         if (kEvents) {
           if (nev < p.events_per_chunk)
-            my_events[nev] = (uint32_t)rel | (o << 16);
+            *my_events = (uint32_t)rel | (o << 16);
+          my_events++; /* a running pointer: no index arithmetic per event */
           nev++;
         }
         if (smem_counts) {
