@@ -88,8 +88,8 @@ struct acm_device_image {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_pairbits, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
-  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_hot_spans, d_events, d_chunk_events, d_small;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_s2_dist, d_kw_dist, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
+  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_tile_spill, d_hot_spans, d_events, d_chunk_events, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
@@ -101,7 +101,7 @@ struct acm_device_image {
     uint32_t prefix[1024];
   } *h_small = nullptr;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
-  bool stride2 = false;   /* the stride-2 tables (bloom_s2, pairbits) are resident */
+  bool stride2 = false;   /* the stride-2 tables (bloom_s2, s2_dist, kw_dist) are resident */
   bool has_rpool = false; /* the reversed keyword pool (kw_meta, kw_rpool) is resident */
   bool prefer_dense = false; /* the last filter scan overflowed its candidate buffers: start the next one in dense mode */
   ACMB200Stats stats = {};
@@ -112,8 +112,8 @@ acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_pairbits, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
-                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_hot_spans, &img->d_events, &img->d_chunk_events, &img->d_small })
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_s2_dist, &img->d_kw_dist, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
+                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_tile_spill, &img->d_hot_spans, &img->d_events, &img->d_chunk_events, &img->d_small })
     b->release ();
   for (cudaEvent_t e : img->ev)
     if (e)
@@ -196,13 +196,14 @@ finalise_locked (ACMachine *m, int device) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (t.bloom2 && (rc = upload (img->d_bloom2, t.bloom2, (size_t)t.bloom2_words * 4, st))) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
         || (rc = upload (img->d_edges, t.edges, t.edge_slots * sizeof (acm_slot), st))
         || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
-        || (t.bloom_s2 && ((rc = upload (img->d_bloom_s2, t.bloom_s2, (size_t)t.bloom_s2_words * 4, st)) || (rc = upload (img->d_pairbits, t.pairbits, (size_t)4 << t.pairbits_log2, st))))
+        || (t.bloom_s2 && ((rc = upload (img->d_bloom_s2, t.bloom_s2, (size_t)t.bloom_s2_words * 4, st)) || (rc = upload (img->d_s2_dist, t.s2_dist, (size_t)4 << t.s2_dist_log2, st))
+                            || (rc = upload (img->d_kw_dist, t.kw_dist, ((size_t)t.nb_keywords + 1) * 2, st))))
         || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
         || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st))
         || (t.kw_meta && ((rc = upload (img->d_kw_meta, t.kw_meta, ((size_t)t.nb_keywords + 1) * 8, st)) || (rc = upload (img->d_kw_rpool, t.kw_rpool, t.kw_rpool_words * 4, st)))))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot) + t.kw_pool_bytes + (uint64_t)t.nb_keywords * 12
-            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0) + (t.bloom_s2 ? (uint64_t)t.bloom_s2_words * 4 + ((uint64_t)4 << t.pairbits_log2) : 0) + (t.kw_meta ? (uint64_t)t.nb_keywords * 8 + t.kw_rpool_words * 4 : 0);
+            + (t.qset ? (uint64_t)16 << (32 - t.qset_shift) : 0) + (t.bloom_s2 ? (uint64_t)t.bloom_s2_words * 4 + ((uint64_t)4 << t.s2_dist_log2) + (uint64_t)t.nb_keywords * 2 : 0) + (t.kw_meta ? (uint64_t)t.nb_keywords * 8 + t.kw_rpool_words * 4 : 0);
   } else {
     if ((rc = upload (img->d_delta, t.delta, t.delta_bytes, st)) || (rc = upload (img->d_out_offsets, t.out_offsets, ((size_t)t.nb_dfa_states - t.out_threshold + 1) * 4, st))
         || (rc = upload (img->d_out_entries, t.out_entries, t.nb_out_entries * sizeof (acm_output), st)))
@@ -220,7 +221,8 @@ finalise_locked (ACMachine *m, int device) {
   free (t.bloom2), t.bloom2 = nullptr;
   img->stride2 = t.bloom_s2 != nullptr;
   free (t.bloom_s2), t.bloom_s2 = nullptr;
-  free (t.pairbits), t.pairbits = nullptr;
+  free (t.s2_dist), t.s2_dist = nullptr;
+  free (t.kw_dist), t.kw_dist = nullptr;
   free (t.qgrams), t.qgrams = nullptr;
   free (t.qset), t.qset = nullptr;
   free (t.kw_len), t.kw_len = nullptr;
@@ -276,6 +278,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++;
   else if (!strcmp (key, "dfa_events")) /* 0: pass 2 of the DFA engines always walks the text again */
     m->option_no_events = !strtoull (value, 0, 10);
+  else if (!strcmp (key, "s2_batches")) /* batches of 32 hits the stride-2 kernel confirms at a time: 1, 2 (default) or 3 */
+    m->option_s2_batches = strtoull (value, 0, 10);
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
     m->option_no_stride2 = !strtoull (value, 0, 10), m->generation++;
   else
@@ -437,7 +441,10 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
 /* ---- filter pipeline ------------------------------------------------------------------------------------------------ */
 enum { kFilterOverflow = 1000 }; /* internal: a candidate buffer overflowed, retry in dense mode */
 
-/* One run of the filter pipeline over job.d_text[0 .. job.n): F1, F2, F3, scan, F4.  Records go to out[0 .. out_cap). */
+/* One run of the filter pipeline over job.d_text[0 .. job.n): F1 (F1s + F1h), F2, F3, scan, F4.  Records go to out[0 .. out_cap).
+ * Nothing between the first and the last kernel waits for the host: the verification kernels run on fixed grids and read the
+ * number of candidates (and of unfinished spans) from device memory; the scalars come back once, after the last kernel.  Only a
+ * scan into the library's own record buffer, which is sized from the total, synchronises before F4. */
 template <int W>
 static int
 run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool dense, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily, uint64_t *total,
@@ -445,168 +452,178 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
   const acm_tables &t = img->tab;
   constexpr int kRowsOpt = 4; /* rows of 512 bytes per warp tile; 2 and 8 were measured slower */
   auto *d_small = img->d_small.as<acm_device_image::Small> ();
-  {
-    FilterParams p = {};
-    p.text = job.d_text;
-    p.n = job.n;
-    p.lead = job.lead;
-    p.base = job.base;
-    p.q = t.q;
-    const bool s2 = W == 1 && !dense && img->stride2; /* stride-2 kernel: its "tiles" for F2..F4 are spans of 2 KiB tiles */
-    p.tile_syms = s2 ? kS2SpanBytes : kRowsOpt * 512 / W;
-    p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
-    p.bloom_s2 = img->d_bloom_s2.as<uint32_t> ();
-    p.bloom_s2_words = t.bloom_s2_words;
-    p.pairbits = img->d_pairbits.as<uint32_t> ();
-    p.pairbits_log2 = t.pairbits_log2;
-    p.span_counter = &d_small->span_counter;
-    p.s2_hit_cap = t.s2_hit_cap;
-    p.hot_count = &d_small->hot_count;
-    p.hot_cap = s2 ? (uint32_t)std::max<uint64_t> (p.ntiles / 8, 64) : 0; /* more unfinished spans than that: the text is dense, use the dense mode */
-    p.bloom = img->d_bloom.as<uint32_t> ();
-    p.bloom_words = t.bloom_words;
-    p.bloom_k = t.bloom_k;
-    p.bloom2 = img->two_level ? img->d_bloom2.as<uint32_t> () : nullptr;
-    p.bloom2_words = t.bloom2_words;
-    p.qgrams = img->d_qgrams.as<acm_slot> ();
-    p.qgram_mask = t.qgram_slots - 1;
-    p.qset = W == 4 ? nullptr : img->d_qset.as<uint4> ();
-    p.qset_shift = t.qset_shift;
-    p.qset_has_empty_key = t.qset_has_empty_key;
-    p.edges = img->d_edges.as<acm_slot> ();
-    p.edge_mask = t.edge_slots - 1;
-    p.kw_len = img->d_kw_len.as<uint32_t> ();
-    p.kw_off = img->d_kw_off.as<uint64_t> ();
-    p.kw_pool = img->d_kw_pool.ptr;
-    p.kw_meta = img->has_rpool ? img->d_kw_meta.as<uint2> () : nullptr;
-    p.kw_rpool = img->d_kw_rpool.as<uint32_t> ();
-    p.prefix = d_small->prefix;
-    p.prefix_len = job.prefix_len;
-    /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */
-    const uint32_t expected_hits = (uint32_t)(t.bloom_fp * p.tile_syms);
-    p.stage_cap = dense ? p.tile_syms : std::min<uint32_t> (p.tile_syms, std::max<uint32_t> (192, 2 * expected_hits + 128));
-    p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / 32, 1u << 16);
-    size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
-    int warps = 32;
-    while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
-      warps /= 2;
-    if (s2)
-      warps = 32;
-    const size_t smem = s2 ? (size_t)t.bloom_s2_words * 4 + 32 * (size_t)ACM_S2_WARP_BYTES (t.s2_hit_cap) : (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp;
-    if (smem > img->smem_optin)
-      return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
-    int rc;
-    if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = img->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
-        || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_hot_spans.ensure ((size_t)p.hot_cap * 4 + 16)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
-      return rc;
-    p.cand_pos = img->d_cand_pos.as<uint64_t> ();
-    p.cand_matches = img->d_cand_matches.as<uint32_t> ();
-    p.cand_prefix = img->d_cand_prefix.as<uint32_t> ();
-    p.cand_inline = img->d_cand_inline.as<uint4> ();
-    p.tile_first = img->d_tile_first.as<uint64_t> ();
-    p.tile_n = img->d_tile_n.as<uint32_t> ();
-    p.hot_spans = img->d_hot_spans.as<uint32_t> ();
-    p.tile_matches = img->d_counts.as<uint32_t> ();
-    p.tile_offsets = img->d_offsets.as<uint64_t> ();
-    p.cand_count = &d_small->cand_count;
-    p.overflow = &d_small->overflow;
+  FilterParams p = {};
+  p.text = job.d_text;
+  p.n = job.n;
+  p.lead = job.lead;
+  p.base = job.base;
+  p.q = t.q;
+  p.lmax = t.lmax;
+  const bool s2 = W == 1 && !dense && img->stride2; /* stride-2 kernel: its "tiles" for F2..F4 are spans of 2 KiB tiles */
+  p.tile_syms = s2 ? kS2SpanBytes : kRowsOpt * 512 / W;
+  p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
+  p.bloom_s2 = img->d_bloom_s2.as<uint32_t> ();
+  p.bloom_s2_words = t.bloom_s2_words;
+  p.s2_dist = img->d_s2_dist.as<uint32_t> ();
+  p.s2_dist_log2 = t.s2_dist_log2;
+  p.kw_dist = s2 ? img->d_kw_dist.as<uint16_t> () : nullptr;
+  p.span_counter = &d_small->span_counter;
+  p.s2_hit_cap = t.s2_hit_cap;
+  p.hot_count = &d_small->hot_count;
+  p.hot_cap = s2 ? (uint32_t)std::max<uint64_t> (p.ntiles / 8, 64) : 0; /* more unfinished spans than that: the text is dense, use the dense mode */
+  p.bloom = img->d_bloom.as<uint32_t> ();
+  p.bloom_words = t.bloom_words;
+  p.bloom_k = t.bloom_k;
+  p.bloom2 = img->two_level ? img->d_bloom2.as<uint32_t> () : nullptr;
+  p.bloom2_words = t.bloom2_words;
+  p.qgrams = img->d_qgrams.as<acm_slot> ();
+  p.qgram_mask = t.qgram_slots - 1;
+  p.qset = W == 4 ? nullptr : img->d_qset.as<uint4> ();
+  p.qset_shift = t.qset_shift;
+  p.qset_has_empty_key = t.qset_has_empty_key;
+  p.edges = img->d_edges.as<acm_slot> ();
+  p.edge_mask = t.edge_slots - 1;
+  p.kw_len = img->d_kw_len.as<uint32_t> ();
+  p.kw_off = img->d_kw_off.as<uint64_t> ();
+  p.kw_pool = img->d_kw_pool.ptr;
+  p.kw_meta = img->has_rpool ? img->d_kw_meta.as<uint2> () : nullptr;
+  p.kw_rpool = img->d_kw_rpool.as<uint32_t> ();
+  p.prefix = d_small->prefix;
+  p.prefix_len = job.prefix_len;
+  /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */
+  const uint32_t expected_hits = (uint32_t)(t.bloom_fp * p.tile_syms);
+  p.stage_cap = dense ? p.tile_syms : std::min<uint32_t> (p.tile_syms, std::max<uint32_t> (192, 2 * expected_hits + 128));
+  /* candidate list (32 bytes of scratch per entry): every position in dense mode; otherwise what a text as sparse in candidates as
+   * the filter assumes needs, with a wide margin -- a denser text overflows it and is redone in dense mode, segment by segment */
+  p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / (s2 ? 256 : 32), 1u << 20);
+  size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
+  int warps = 32;
+  while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
+    warps /= 2;
+  if (s2)
+    warps = 32;
+  const size_t smem = s2 ? (size_t)t.bloom_s2_words * 4 + 32 * (size_t)ACM_S2_WARP_BYTES (t.s2_hit_cap) : (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp;
+  if (smem > img->smem_optin)
+    return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
+  int rc;
+  if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = img->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
+      || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_tile_spill.ensure (p.ntiles * 4)) || (rc = img->d_hot_spans.ensure ((size_t)p.hot_cap * 4 + 16)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
+    return rc;
+  p.cand_pos = img->d_cand_pos.as<uint64_t> ();
+  p.cand_matches = img->d_cand_matches.as<uint32_t> ();
+  p.cand_prefix = img->d_cand_prefix.as<uint32_t> ();
+  p.cand_inline = img->d_cand_inline.as<uint4> ();
+  p.tile_first = img->d_tile_first.as<uint64_t> ();
+  p.tile_n = img->d_tile_n.as<uint32_t> ();
+  p.tile_spill = s2 ? img->d_tile_spill.as<uint32_t> () : nullptr;
+  p.hot_spans = img->d_hot_spans.as<uint32_t> ();
+  p.tile_matches = img->d_counts.as<uint32_t> ();
+  p.tile_offsets = img->d_offsets.as<uint64_t> ();
+  p.cand_count = &d_small->cand_count;
+  p.overflow = &d_small->overflow;
 
-    void (*f1) (const FilterParams) = nullptr;
-    const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
-    const int K = 2; /* bits per key; 3 was measured slower, the kernels keep K as a template parameter */
+  void (*f1) (const FilterParams) = nullptr;
+  const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
+  const int K = 2; /* bits per key; 3 was measured slower, the kernels keep K as a template parameter */
 #define ACM_F1_(Q_, K_, R_)                                                                                                                      \
   (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, true> : filter_scan_kernel<W, R_, Q_, K_, false, true>)       \
             : (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, false> : filter_scan_kernel<W, R_, Q_, K_, false, false>))
 #define ACM_F1(Q_, K_)                                                                                                                           \
   if (p.q == Q_ && K == K_)                                                                                                                      \
     f1 = ACM_F1_ (Q_, K_, kRowsOpt)
-    ACM_F1 (1, 2); ACM_F1 (2, 2);
-    if (W == 1) {
-      ACM_F1 (3, 2); ACM_F1 (4, 2);
-    }
+  ACM_F1 (1, 2); ACM_F1 (2, 2);
+  if (W == 1) {
+    ACM_F1 (3, 2); ACM_F1 (4, 2);
+  }
 #undef ACM_F1
 #undef ACM_F1_
-    if (s2) /* 2 bits per key, 3 x 32 hits confirmed at a time, 4 rows per tile: the measured optimum */
-      f1 = filter_scan_s2_kernel<2, 3, 4>;
-    if (!f1)
-      return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
-    CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    img->stats.smem_bytes = smem;
-    img->stats.filter_stride = s2 ? 2 : 1;
-    /* header of Small (cand_count, grand_total, overflow) cleared; the prefix symbols follow */
-    img->h_small->cand_count = 0;
-    img->h_small->grand_total = 0;
-    img->h_small->overflow = 0;
-    img->h_small->span_counter = 0;
-    img->h_small->hot_count = 0;
-    CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
-    const unsigned grid = (unsigned)std::min<uint64_t> (((s2 ? (job.n + 2047) / 2048 : p.ntiles) + warps - 1) / warps, (uint64_t)img->sm_count);
-    if (first_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
-    f1<<<grid, warps * 32, smem, job.st>>> (p);
+  if (s2) /* 2 bits per key, kBatches x 32 hits confirmed at a time, 4 rows per tile: the measured optimum */
+    f1 = m->option_s2_batches == 1 ? filter_scan_s2_kernel<2, 1, 4> : (m->option_s2_batches == 3 ? filter_scan_s2_kernel<2, 3, 4> : filter_scan_s2_kernel<2, 2, 4>);
+  if (!f1)
+    return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
+  CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  img->stats.smem_bytes = smem;
+  img->stats.filter_stride = s2 ? 2 : 1;
+  /* header of Small (cand_count, grand_total, overflow, ...) cleared; the prefix symbols follow */
+  img->h_small->cand_count = 0;
+  img->h_small->grand_total = 0;
+  img->h_small->overflow = 0;
+  img->h_small->span_counter = 0;
+  img->h_small->hot_count = 0;
+  CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
+  const unsigned grid = (unsigned)std::min<uint64_t> (((s2 ? (job.n + 2047) / 2048 : p.ntiles) + warps - 1) / warps, (uint64_t)img->sm_count);
+  if (first_segment)
+    CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+  f1<<<grid, warps * 32, smem, job.st>>> (p);
+  CUDA_TRY (cudaGetLastError ());
+  if (first_segment)
+    CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
+  img->stats.main_kernel_launches += 1;
+  img->stats.total_kernel_launches += 1;
+  if (s2) { /* the spans whose stages overflowed are redone exactly; usually there are none and the kernel ends at once */
+    CUDA_TRY (cudaFuncSetAttribute (filter_hot_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHotSmemBytes));
+    filter_hot_spans_kernel<<<(unsigned)std::min<uint64_t> (p.hot_cap, (uint64_t)img->sm_count * 2), 32, kHotSmemBytes, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
-    if (first_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
-    /* the number of candidates decides the grid of the verification kernels (and tells whether a buffer overflowed) */
+    img->stats.total_kernel_launches += 1;
+  }
+  const unsigned vgrid = (unsigned)std::min<uint64_t> ((p.cand_cap + 255) / 256, (uint64_t)img->sm_count * 8), tgrid = (unsigned)((p.ntiles + 255) / 256);
+  filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p);
+  CUDA_TRY (cudaGetLastError ());
+  filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
+  CUDA_TRY (cudaGetLastError ());
+  img->stats.total_kernel_launches += 2;
+  if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+    return rc;
+  /* the scalars the kernels wrote: overflow flags, number of candidates / unfinished spans, grand total */
+  auto fetch_small = [&] () -> int {
     CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
     CUDA_TRY (cudaStreamSynchronize (job.st));
-    img->stats.main_kernel_launches += 1;
-    img->stats.total_kernel_launches += 1;
-    if (img->h_small->overflow) {
+    if (img->h_small->overflow || (s2 && img->h_small->hot_count > p.hot_cap)) {
       if (dense)
         return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
       return kFilterOverflow;
     }
-    if (s2 && img->h_small->hot_count) {
-      /* a few spans overflowed the stride-2 kernel's stages: they are redone exactly, everything else stands */
-      const uint32_t nb_hot = img->h_small->hot_count;
-      if (nb_hot > p.hot_cap)
-        return kFilterOverflow;
-      filter_hot_spans_kernel<<<(nb_hot + kHotWarps - 1) / kHotWarps, kHotWarps * 32, 0, job.st>>> (p, nb_hot);
-      CUDA_TRY (cudaGetLastError ());
-      CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
-      CUDA_TRY (cudaStreamSynchronize (job.st));
-      img->stats.total_kernel_launches += 1;
-      img->stats.hot_spans += nb_hot;
-      if (img->h_small->overflow)
-        return kFilterOverflow;
-    }
-    const uint64_t nb_cand = img->h_small->cand_count;
-    const unsigned vgrid = (unsigned)((nb_cand + 255) / 256), tgrid = (unsigned)((p.ntiles + 255) / 256);
-    if (nb_cand) {
-      filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p, nb_cand);
-      CUDA_TRY (cudaGetLastError ());
-      img->stats.total_kernel_launches += 1;
-    }
-    filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
+    return ACM_B200_OK;
+  };
+  auto emit = [&] (uint64_t cap) -> int {
+    p.matches = out;
+    p.capacity = cap;
+    filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
     img->stats.total_kernel_launches += 1;
-    if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+    return ACM_B200_OK;
+  };
+  if (size_out_lazily) { /* single run into the library's own buffer: sized now that the total is known */
+    if ((rc = fetch_small ()))
       return rc;
-    CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
-    CUDA_TRY (cudaStreamSynchronize (job.st));
-    *total = img->h_small->grand_total;
-    img->stats.last_nb_candidates += nb_cand;
-    const uint64_t want = std::min<uint64_t> (*total, out_cap);
+    const uint64_t want = std::min<uint64_t> (img->h_small->grand_total, out_cap);
     if (last_segment)
       CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
     if (want) {
-      if (size_out_lazily) { /* single run into the library's own buffer: sized now that the total is known */
-        if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
-          return rc;
-        out = img->d_matches.as<ACMB200Match> ();
-      }
-      p.matches = out;
-      p.capacity = want;
-      filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p, nb_cand);
-      CUDA_TRY (cudaGetLastError ());
-      img->stats.total_kernel_launches += 1;
+      if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
+        return rc;
+      out = img->d_matches.as<ACMB200Match> ();
+      if ((rc = emit (want)))
+        return rc;
     }
     if (last_segment)
       CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
-    *out_used = out;
-    return ACM_B200_OK;
+  } else { /* the record buffer is known: F4 writes what fits, the host looks at the scalars once everything is queued */
+    if (last_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+    if (out_cap && out && (rc = emit (out_cap)))
+      return rc;
+    if (last_segment)
+      CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+    if ((rc = fetch_small ()))
+      return rc;
   }
+  *total = img->h_small->grand_total;
+  img->stats.last_nb_candidates += img->h_small->cand_count;
+  if (s2)
+    img->stats.hot_spans += img->h_small->hot_count;
+  *out_used = out;
+  return ACM_B200_OK;
 }
 
 /* Filter engine: one run over the whole text; if a candidate buffer overflows (text much denser in candidates than the filter's
@@ -914,8 +931,9 @@ acm_b200_generate_text (void *dst, int dst_on_device, uint64_t first, uint64_t n
     g.dict_symbols = reinterpret_cast<const uint8_t *> (d_sym);
     g.dict_offsets = reinterpret_cast<const uint64_t *> (d_off);
   }
-  int sms = 148;
-  cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, 0);
+  int sms = 148, dev = 0;
+  cudaGetDevice (&dev);
+  cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
   generate_text_kernel<<<sms * 8, 256, 0, st>>> (g);
   CUDA_TRY (cudaGetLastError ());
   CUDA_TRY (cudaStreamSynchronize (st));

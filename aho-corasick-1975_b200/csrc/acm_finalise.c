@@ -160,7 +160,8 @@ acm_free_tables (struct acm_tables *t) {
   free (t->bloom);
   free (t->bloom2);
   free (t->bloom_s2);
-  free (t->pairbits);
+  free (t->s2_dist);
+  free (t->kw_dist);
   free (t->qgrams);
   free (t->qset);
   free (t->kw_len);
@@ -260,6 +261,217 @@ build_dfa (struct _ac_machine *m, struct acm_tables *t, struct _ac_state **by_de
   }
   free (of_dfa);
   return ACM_B200_OK;
+}
+
+/* ---- stride-2 filter: window choice ------------------------------------------------------------------------------ */
+/* Every keyword without a proper suffix that is a keyword ("root") chooses, for each parity, the distance d of the 3-byte window
+ * it puts into the shared-memory filter (acm_tables.h); the others inherit the distances of their longest suffix keyword (the
+ * same bytes, hence the same filter bits and the same distance-table entries).  Choice = the window that adds the fewest new
+ * bits, weighted towards emptier filter words (the false-positive rate is the mean of the squared word fills), refined by
+ * re-choosing every window a few times against a counting filter. */
+struct s2_build {
+  uint32_t words;
+  uint32_t *cnt; /* [words][32] keys per bit */
+  uint8_t *pop;  /* [words] bits set */
+};
+
+static inline void
+s2_bits_of (uint32_t key, uint32_t words, uint32_t *word, uint32_t *b0, uint32_t *b1) {
+  const uint32_t mask = acm_bloom_mask (key, 2);
+  *word = acm_bloom_word (key, words);
+  *b0 = (uint32_t)__builtin_ctz (mask);
+  *b1 = 31u - (uint32_t)__builtin_clz (mask); /* == b0 when both hash bits coincide */
+}
+
+static void
+s2_apply (struct s2_build *b, uint32_t key, int add) {
+  uint32_t w, b0, b1;
+  s2_bits_of (key, b->words, &w, &b0, &b1);
+  for (int i = 0; i < (b0 == b1 ? 1 : 2); i++) {
+    uint32_t *c = &b->cnt[(size_t)w * 32 + (i ? b1 : b0)];
+    if (add) {
+      if ((*c)++ == 0)
+        b->pop[w]++;
+    } else if (--(*c) == 0)
+      b->pop[w]--;
+  }
+}
+
+static uint32_t
+s2_cost (const struct s2_build *b, uint32_t key) {
+  uint32_t w, b0, b1;
+  s2_bits_of (key, b->words, &w, &b0, &b1);
+  uint32_t fresh = b->cnt[(size_t)w * 32 + b0] == 0;
+  if (b1 != b0)
+    fresh += b->cnt[(size_t)w * 32 + b1] == 0;
+  const uint32_t c = b->pop[w];
+  return (c + fresh) * (c + fresh) - c * c;
+}
+
+/* window of keyword bytes k[0..len) whose last byte lies d bytes before the keyword's last byte */
+static inline uint32_t
+s2_window_key (const uint8_t *k, uint32_t len, uint32_t d) {
+  const uint8_t *w = k + len - 3 - d;
+  return acm_s2_key (w[0], w[1], w[2]);
+}
+
+static void
+s2_dist_insert (uint32_t *tab, uint32_t lg, uint32_t gram3, uint32_t entry /* VALID | RIGHT? | d << 8 | ext */) {
+  const uint32_t mask = (1u << lg) - 1u;
+  for (uint32_t idx = acm_pair_word (gram3, lg);; idx = (idx + 1) & mask) {
+    const uint32_t lo = tab[idx] & 0xFFFFu, hi = tab[idx] >> 16;
+    if ((lo & ~ACM_S2D_CONT) == entry || hi == entry)
+      return; /* shared with another keyword */
+    if (!(lo & ACM_S2D_VALID)) {
+      tab[idx] |= entry;
+      return;
+    }
+    if (!(hi & ACM_S2D_VALID)) {
+      tab[idx] |= entry << 16;
+      return;
+    }
+    tab[idx] |= ACM_S2D_CONT;
+  }
+}
+
+static int
+build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin) {
+  const uint32_t nk = t->nb_keywords;
+  const uint8_t *pool = t->kw_pool;
+  int rc = ACM_B200_ERR_NOMEM;
+  uint32_t *parent = malloc ((size_t)nk * sizeof (uint32_t)), *order = malloc ((size_t)nk * sizeof (uint32_t));
+  uint32_t *start = calloc ((size_t)t->lmax + 2, sizeof (uint32_t));
+  uint8_t *dist = malloc ((size_t)nk * 2);
+  struct s2_build b = { 0, 0, 0 };
+  uint32_t *bl = 0;
+  if (!parent || !order || !start || !dist)
+    goto done;
+  /* longest proper suffix that is a keyword: the first terminal state on the fail chain (Appendix C rule 4) */
+  for (uint32_t r = 0; r < nk; r++) {
+    parent[r] = ACM_NONE;
+    const struct _ac_state *s = m->keywords[r];
+    if (s->nb_outputs > 1)
+      for (const struct _ac_state *f = s->fail; f && f->parent; f = f->fail)
+        if (f->rank != ACM_NONE) {
+          parent[r] = f->rank;
+          break;
+        }
+  }
+  /* keywords by ascending length (a suffix keyword comes before the keywords that inherit from it) */
+  for (uint32_t r = 0; r < nk; r++)
+    start[t->kw_len[r] + 1]++;
+  for (uint32_t l = 0; l <= t->lmax; l++)
+    start[l + 1] += start[l];
+  for (uint32_t r = 0; r < nk; r++)
+    order[start[t->kw_len[r]]++] = r;
+  uint64_t roots = 0;
+  for (uint32_t r = 0; r < nk; r++)
+    roots += parent[r] == ACM_NONE;
+
+  /* The stage capacity depends on the hit rate, which depends on the filter size, which is what the stages leave of the shared
+   * memory the kernel may use (smem_optin here): start from a small stage and grow it until the expected hits fit with a margin. */
+  uint32_t hit_cap = 64;
+  for (int attempt = 0; attempt < 10; attempt++, hit_cap += 32) {
+    const uint64_t room = smem_optin - 2048;
+    if (room < 32ull * ACM_S2_WARP_BYTES (hit_cap) + 4096)
+      break;
+    const uint64_t s2_max = (room - 32ull * ACM_S2_WARP_BYTES (hit_cap)) / 4;
+    uint64_t s2_want = m->option_bloom_words ? m->option_bloom_words : pow2_at_least ((2ull * nk * 24 + 31) / 32);
+    if (s2_want > s2_max)
+      s2_want = s2_max;
+    if (s2_want < 64)
+      s2_want = 64;
+    if (b.words != (uint32_t)s2_want) {
+      free (b.cnt);
+      free (b.pop);
+      b.words = (uint32_t)s2_want;
+      b.cnt = calloc ((size_t)b.words * 32, sizeof (uint32_t));
+      b.pop = calloc (b.words, 1);
+      if (!b.cnt || !b.pop)
+        goto done;
+      memset (dist, 0xFF, (size_t)nk * 2);
+      for (int pass = 0; pass < 4; pass++)
+        for (uint32_t i = 0; i < nk; i++) {
+          const uint32_t r = order[i], len = t->kw_len[r];
+          if (parent[r] != ACM_NONE)
+            continue;
+          const uint8_t *k = pool + t->kw_off[r];
+          const uint32_t dmax = len - 3 < ACM_S2_DMAX ? len - 3 : ACM_S2_DMAX;
+          for (uint32_t role = 0; role < 2; role++) {
+            uint8_t *chosen = &dist[2 * (size_t)r + role];
+            if (*chosen != 0xFF)
+              s2_apply (&b, s2_window_key (k, len, *chosen), 0);
+            uint32_t best_d = role, best = 0xFFFFFFFFu;
+            for (uint32_t d = role; d <= dmax; d += 2) {
+              const uint32_t c = s2_cost (&b, s2_window_key (k, len, d)) * 64 + d; /* ties: the window nearest to the end */
+              if (c < best)
+                best = c, best_d = d;
+            }
+            *chosen = (uint8_t)best_d;
+            s2_apply (&b, s2_window_key (k, len, best_d), 1);
+          }
+        }
+    }
+    double fp2 = 0;
+    for (uint32_t i = 0; i < b.words; i++) {
+      const double f = b.pop[i] / 32.0;
+      fp2 += f * f;
+    }
+    const double hit_rate = fp2 / b.words + 2.0 * (double)roots / 16777216.0;
+    if (hit_rate * 1024 * 1.5 + 32 > hit_cap)
+      continue; /* expected hits per tile (1024 tests) must leave a 1.5x margin in the stage */
+    for (uint32_t i = 0; i < nk; i++) { /* ascending length: the suffix keyword's distances are final */
+      const uint32_t r = order[i];
+      if (parent[r] != ACM_NONE) {
+        dist[2 * (size_t)r] = dist[2 * (size_t)parent[r]];
+        dist[2 * (size_t)r + 1] = dist[2 * (size_t)parent[r] + 1];
+      }
+    }
+    bl = calloc (b.words, sizeof (uint32_t));
+    uint32_t lg = 16;
+    while (lg < 24 && (1ull << lg) < 32ull * nk)
+      lg++;
+    t->s2_dist = calloc ((size_t)1 << lg, sizeof (uint32_t));
+    t->kw_dist = malloc (((size_t)nk + 1) * sizeof (uint16_t));
+    if (!bl || !t->s2_dist || !t->kw_dist)
+      goto done;
+    for (uint32_t w = 0; w < b.words; w++)
+      for (uint32_t bit = 0; bit < 32; bit++)
+        if (b.cnt[(size_t)w * 32 + bit])
+          bl[w] |= 1u << bit;
+    t->s2_dist_log2 = lg;
+    for (uint32_t r = 0; r < nk; r++) {
+      t->kw_dist[r] = (uint16_t)(dist[2 * (size_t)r] | (dist[2 * (size_t)r + 1] << 8));
+      if (parent[r] != ACM_NONE)
+        continue;
+      const uint32_t len = t->kw_len[r];
+      const uint8_t *k = pool + t->kw_off[r];
+      for (uint32_t role = 0; role < 2; role++) {
+        const uint32_t d = dist[2 * (size_t)r + role];
+        const uint8_t *w = k + len - 3 - d; /* the window; extended to the left when a keyword byte precedes it, else to the right */
+        const uint32_t gram3 = w[0] | ((uint32_t)w[1] << 8) | ((uint32_t)w[2] << 16);
+        const uint32_t entry = d + 4 <= len ? (ACM_S2D_VALID | (d << 8) | w[-1]) : (ACM_S2D_VALID | ACM_S2D_RIGHT | (d << 8) | w[3]);
+        s2_dist_insert (t->s2_dist, lg, gram3, entry);
+      }
+    }
+    t->bloom_s2 = bl;
+    bl = 0;
+    t->bloom_s2_words = b.words;
+    t->bloom_s2_k = 2; /* bits per key; 3 was measured slower at every filter size */
+    t->bloom_s2_hit_rate = hit_rate;
+    t->s2_hit_cap = hit_cap;
+    break;
+  }
+  rc = ACM_B200_OK;
+done:
+  free (parent);
+  free (order);
+  free (start);
+  free (dist);
+  free (b.cnt);
+  free (b.pop);
+  free (bl);
+  return rc;
 }
 
 /* ---- filter engine -------------------------------------------------------------------------------------------------- */
@@ -481,68 +693,11 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
   /* stride-2 filter (acm_tables.h): byte alphabet, every keyword at least 4 bytes long, dictionary small enough for the
    * shared-memory level to stay selective with two keys per keyword */
   if (t->width == 1 && q == 4 && nk && !t->bloom2 && smem_optin >= 65536) {
-    /* smem_optin here = the shared memory the stride-2 kernel may use in total (filter + per-warp stages).  The stage capacity
-     * depends on the hit rate, which depends on the filter size: start from a small stage and grow it until it fits. */
-    const uint8_t *pool = t->kw_pool;
-    const uint32_t s2k = 2; /* bits per key; 3 was measured slower at every filter size */
-    uint32_t *bl = 0;
-    uint32_t words = 0, hit_cap = 96;
-    double hit_rate = 1;
-    for (int attempt = 0; attempt < 8; attempt++, hit_cap += 32) {
-      const uint64_t room = smem_optin - 2048;
-      if (room < 32ull * ACM_S2_WARP_BYTES (hit_cap) + 4096)
-        break;
-      const uint64_t s2_max = (room - 32ull * ACM_S2_WARP_BYTES (hit_cap)) / 4;
-      uint64_t s2_want = m->option_bloom_words ? m->option_bloom_words : pow2_at_least ((2ull * nk * 24 + 31) / 32);
-      if (s2_want > s2_max)
-        s2_want = s2_max;
-      if (s2_want < 64)
-        s2_want = 64;
-      if (!bl || (uint32_t)s2_want != words) {
-        free (bl);
-        words = (uint32_t)s2_want;
-        bl = calloc (words, sizeof (uint32_t));
-        if (!bl)
-          goto done;
-        for (uint32_t r = 0; r < nk; r++) {
-          const uint8_t *k = pool + t->kw_off[r] + t->kw_len[r] - 4; /* the last four bytes */
-          const uint32_t a = acm_s2_key (k[1], k[2], k[3]), b = acm_s2_key (k[0], k[1], k[2]);
-          bl[acm_bloom_word (a, words)] |= acm_bloom_mask (a, s2k);
-          bl[acm_bloom_word (b, words)] |= acm_bloom_mask (b, s2k);
-        }
-        double fp2 = 0;
-        for (uint32_t i = 0; i < words; i++) {
-          const double f = __builtin_popcount (bl[i]) / 32.0;
-          fp2 += s2k > 2 ? f * f * f : f * f;
-        }
-        hit_rate = fp2 / words + 2.0 * nk / 16777216.0;
-      }
-      if (hit_rate * 1024 * 1.5 + 32 <= hit_cap) { /* expected hits per tile (1024 tests) leave a 1.5x margin in the stage */
-        uint32_t lg = 16;
-        while (lg < 24 && (1ull << lg) < 32ull * nk)
-          lg++;
-        t->pairbits = calloc ((size_t)1 << lg, sizeof (uint32_t));
-        if (!t->pairbits) {
-          free (bl);
-          goto done;
-        }
-        t->pairbits_log2 = lg;
-        for (uint32_t r = 0; r < nk; r++) {
-          const uint8_t *k = pool + t->kw_off[r] + t->kw_len[r] - 4;
-          const uint32_t win4 = k[0] | ((uint32_t)k[1] << 8) | ((uint32_t)k[2] << 16) | ((uint32_t)k[3] << 24);
-          t->pairbits[acm_pair_word (win4 >> 8, lg)] |= acm_pair_mask (win4, 0);         /* ends on the sampled position */
-          t->pairbits[acm_pair_word (win4 & 0xFFFFFFu, lg)] |= acm_pair_mask (win4, 1);  /* ends one after it */
-        }
-        t->bloom_s2 = bl;
-        t->bloom_s2_words = words;
-        t->bloom_s2_k = s2k;
-        t->bloom_s2_hit_rate = hit_rate;
-        t->s2_hit_cap = hit_cap;
-        bl = 0;
-        break;
-      }
+    const int s2rc = build_stride2 (m, t, smem_optin);
+    if (s2rc != ACM_B200_OK) {
+      rc = s2rc;
+      goto done;
     }
-    free (bl);
   }
   rc = ACM_B200_OK;
 done:

@@ -88,7 +88,7 @@ struct _ac_machine {
   char engine_override[16];
   uint64_t option_bloom_words, option_threads, option_stream_bytes;
   int option_no_stride2, option_no_events;
-  uint64_t option_s2_smem_kb;
+  uint64_t option_s2_smem_kb, option_s2_batches;
 };
 
 /* acm_host.c */

@@ -192,7 +192,7 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
 
     /* positions are walked relative to the chunk start, in 32 bits (negative during the warm-up): the per-byte test is one
      * compare, and the recorded event needs no 64-bit arithmetic */
-    const int32_t report_rel = (int32_t)(report_from - start);
+    const int32_t report_rel = (int32_t)min (report_from - start, p.chunk); /* a chunk wholly before `lead` never reports */
     auto step = [&] (uint32_t byte, int32_t rel) {
       state = delta[state * K + s_class[byte]];
       if (state >= thr && rel >= report_rel) {
@@ -531,8 +531,11 @@ struct FilterParams {
    * (tile_syms, ntiles, tile_first, tile_n) are the spans. */
   const uint32_t *bloom_s2;
   uint32_t bloom_s2_words;
-  const uint32_t *pairbits;
-  uint32_t pairbits_log2;
+  const uint32_t *s2_dist;   /* distance table (acm_tables.h), 1 << s2_dist_log2 words */
+  uint32_t s2_dist_log2;
+  const uint16_t *kw_dist;   /* keyword id -> chosen distances dA | dB << 8 (null: candidates carry no distance mask) */
+  uint32_t lmax;             /* longest keyword */
+  uint32_t *tile_spill;      /* F1s/F1h out (else null): how many of a span's candidates, the last ones, END in the next span */
   uint32_t s2_hit_cap;
   uint32_t *hot_spans;      /* spans F1s could not finish (a stage overflowed): redone exactly by filter_hot_spans_kernel */
   uint32_t hot_cap;
@@ -683,7 +686,8 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   uint4 v[kRows];
   uint32_t before_tile = 0;
   const uint64_t tile_stride = (uint64_t)gridDim.x * warps;
-  auto interior_tile = [&] (uint64_t t) { return t * kTileSyms >= first_valid + 4 && (t + 1) * kTileSyms <= p.n; };
+  /* interior also means: the aligned word after the tile is inside the text (the confirmation step reads it for the tile's last symbols) */
+  auto interior_tile = [&] (uint64_t t) { return t * kTileSyms >= first_valid + 4 && (t + 1) * kTileSyms + 4 <= p.n; };
   auto load_tile = [&] (uint64_t t) {
     const uint64_t base = t * kTileSyms;
     const uint8_t *ptr = text8 + base * W;
@@ -928,15 +932,38 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
 /* F1s: the stride-2 variant of F1 for byte alphabets whose shortest keyword has at least 4 bytes (acm_tables.h).
  *
  * Only the even offsets of a tile are tested, each on the 3-byte window ending there: 8 tests per lane and 512-byte row instead
- * of 16, built with one byte permute each (one shared-memory lookup per TWO text bytes).  A hit at the sampled position s names two
- * candidate end positions, s and s+1.  Hits are staged as (lane, test index), slots from a warp scan; the confirmation step re-reads
- * the 5 bytes s-3..s+1 (usually still in L1: the tile loads are evict_last and the kernel leaves ~60 KB of the SM to L1), loads ONE
- * word of the second-level table (L2, ld.global.cg; indexed by the 3-byte window, two bits per role and 4-byte window) and keeps the
- * few survivors.  A warp works through a span of consecutive tiles taken from a global counter and appends the span's candidates, in
- * position order, with one reservation -- so F2..F4 see spans where they saw tiles.  F2 verifies candidates exactly, so everything
- * here may err on the side of keeping a position; nothing may drop one.
- * Measured cost split on config 3: filter tests 2.1 ms per 8 GiB, staging 0.4 ms, confirmation 1.2 ms. */
+ * of 16, built with one byte permute each (one shared-memory lookup per TWO text bytes).  The filter holds, for every keyword, the
+ * two windows the finalise step chose for it; a hit at the sampled position s is confirmed in the distance table (L2, one word
+ * load, ld.global.cg): an entry that matches the window's extension byte says that a keyword may END at s + d.  Hits are staged as
+ * (lane, test index), slots from a warp scan; the confirmation re-reads the 5 bytes s-3..s+1 (usually still in L1: the tile
+ * loads are evict_last and the kernel leaves ~60 KB of the SM to L1).  A warp works through a span of consecutive tiles taken
+ * from a global counter, sorts the span's candidates by end position (merging the distance masks of equal ends) and appends them
+ * with one reservation -- so F2..F4 see spans where they saw tiles; the candidates whose end lies in the NEXT span come last and
+ * are counted in tile_spill, F3 merges them into the next span's order.  F2 verifies candidates exactly, so everything here may
+ * err on the side of keeping a position; nothing may drop one. */
 constexpr uint32_t kS2SpanBytes = 32768;
+constexpr uint32_t kS2EndSlack = 32; /* a candidate end lies at most ACM_S2_DMAX bytes after its sampled position */
+
+/* Exact (slow) form of the confirmation, for the first / last tile and for the spans redone by filter_hot_spans_kernel:
+ * calls emit (d) for every distance-table entry that matches the window ending at the sampled position s (2 <= s < n). */
+template <typename F>
+__device__ __forceinline__ void
+s2_probe (const FilterParams &p, const uint8_t *text8, uint64_t s, F &&emit) {
+  const uint32_t gram3 = (uint32_t)text8[s - 2] | ((uint32_t)text8[s - 1] << 8) | ((uint32_t)text8[s] << 16);
+  const int left = s >= 3 ? (int)text8[s - 3] : -1, right = s + 1 < p.n ? (int)text8[s + 1] : -1;
+  const uint32_t mask = (1u << p.s2_dist_log2) - 1u;
+  for (uint32_t idx = acm_pair_word (gram3, p.s2_dist_log2);; idx = (idx + 1) & mask) {
+    const uint32_t word = __ldcg (p.s2_dist + idx);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t ent = (word >> (16 * h)) & 0xFFFFu;
+      if ((ent & ACM_S2D_VALID) && ((ent & ACM_S2D_RIGHT) ? right : left) == (int)(ent & 0xFFu))
+        emit (ACM_S2D_DIST (ent));
+    }
+    if (!(word & ACM_S2D_CONT))
+      break;
+  }
+}
 
 template <int K, int kBatches, int kRows>
 __global__ void __launch_bounds__ (1024, 1)
@@ -953,22 +980,23 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t kHitCap = p.s2_hit_cap; /* 1.5x the expected hits per tile + 32, see acm_finalise.c */
   unsigned char *mine = smem + (size_t)p.bloom_s2_words * 4 + (size_t)warp * ACM_S2_WARP_BYTES (kHitCap);
+  uint32_t *slow_count = reinterpret_cast<uint32_t *> (mine); /* candidate counter of the slow (first / last tile) path */
   uint16_t *hits = reinterpret_cast<uint16_t *> (mine + 16);
-  uint32_t *cands = reinterpret_cast<uint32_t *> (mine + 16 + kHitCap * 2);
+  uint32_t *cands = reinterpret_cast<uint32_t *> (mine + 16 + kHitCap * 2); /* (span-relative end << 15) | distance mask */
   __syncthreads ();
 
   const uint32_t nwords = p.bloom_s2_words;
   const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
-  const uint32_t pair_shift = 32 - p.pairbits_log2;
-  const uint64_t first_end = max (p.lead, (uint64_t)3); /* ends before it: none without a carried prefix, else listed below */
+  const uint32_t dist_shift = 32 - p.s2_dist_log2, dist_mask = (1u << p.s2_dist_log2) - 1u;
   const uint64_t ntiles = (p.n + kTileBytes - 1) / kTileBytes;
   uint4 v[kRows];
   uint32_t before_tile = 0;
-  auto interior_tile = [&] (uint64_t t) { return t * kTileBytes >= first_end + 1 && (t + 1) * kTileBytes <= p.n; };
+  /* interior: every candidate end of the tile is reportable and inside the text, every window is preceded by text */
+  auto interior_tile = [&] (uint64_t t) { return t * kTileBytes >= max (p.lead, (uint64_t)4) && (t + 1) * kTileBytes + kS2EndSlack <= p.n; };
   auto load_tile = [&] (uint64_t t) {
     const uint64_t base = t * kTileBytes;
     const uint8_t *ptr = text8 + base;
-    if (interior_tile (t)) {
+    if (base >= 4 && (t + 1) * kTileBytes <= p.n) {
 #pragma unroll
       for (int r = 0; r < kRows; r++) /* evict_last: the confirmation step re-reads a few words of the tile one iteration later */
         asm volatile ("ld.global.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "l"(ptr + r * 512 + lane * 16));
@@ -1004,15 +1032,31 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
     if (span >= p.ntiles)
       break;
     const uint64_t tile0 = span * kSpanTiles, tile1 = min (ntiles, tile0 + kSpanTiles);
-    uint32_t ncand = 0; /* warp-uniform: candidates of this span held in cands[], span-relative positions, ordered */
+    uint32_t ncand = 0; /* warp-uniform: candidates of this span held in cands[], in no particular order until the span is done */
     bool hot = false;   /* warp-uniform: a stage of this span overflowed, the span is left to filter_hot_spans_kernel */
     load_tile (tile0);
 
-    for (uint64_t tile = tile0; tile < tile1; tile++) {
+    /* occurrences that begin in the carried-cursor prefix end within the first lmax - 1 positions: those ends are candidates
+     * for every distance (F2 decides) */
+    if (span == 0 && p.prefix_len) {
+      const uint64_t last = min ((uint64_t)(p.lmax ? p.lmax - 1 : 0), p.n);
+      for (uint64_t e0 = p.lead; e0 < last; e0 += 32) {
+        const uint64_t e = e0 + lane;
+        const bool keep = e < last;
+        const uint32_t m = __ballot_sync (kFull, keep);
+        const uint32_t at = ncand + __popc (m & lanes_below);
+        if (keep && at < ACM_S2_CAND_CAP)
+          cands[at] = ((uint32_t)e << 15) | ACM_S2_DMASK_ALL;
+        ncand += __popc (m);
+      }
+      __syncwarp ();
+    }
+
+    hot = ncand > ACM_S2_CAND_CAP;
+    for (uint64_t tile = tile0; tile < tile1 && !hot; tile++) {
       const uint64_t tile_base = tile * kTileBytes;
       const bool interior = interior_tile (tile);
       const uint32_t tile_off = (uint32_t)(tile - tile0) * kTileBytes;
-      const uint32_t tile_first_cand = ncand;
       if (tile + 2 < tile1 && lane < kRows * 4)
         asm volatile ("prefetch.global.L2 [%0];" ::"l"(text8 + (tile + 2) * kTileBytes + lane * 128));
 
@@ -1043,15 +1087,14 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         }
       }
 
-      if (!interior) { /* first / last tile: drop the tests on positions outside the text (zero padding: a thousand equal keys) or
-                          whose two candidate ends both lie before the first reportable one */
+      if (!interior) { /* first / last tile: drop the tests whose window is not wholly inside the text (zero padding: a thousand equal keys) */
 #pragma unroll
         for (int a = 0; a < kAcc; a++) {
           uint32_t keep = 0;
           for (int i = 0; i < 32 && a * 32 + i < 8 * kRows; i++) {
             const uint32_t ti = a * 32 + i;
             const uint64_t s = tile_base + (uint64_t)lane * 16 + (uint64_t)(ti >> 3) * 512 + (ti & 7u) * 2;
-            if (s < p.n && s + 1 >= first_end)
+            if (s >= 2 && s < p.n)
               keep |= 0x80000000u >> i;
           }
           acc[a] &= keep >> kAccShift;
@@ -1059,7 +1102,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       }
 
       /* ---- stage the hits as (lane << 6) | test index; slots from a warp scan of the per-lane counts (a shared counter would
-       * serialise the ~28 lanes that have hits on one bank) ---- */
+       * serialise the lanes that have hits on one bank) ---- */
       uint32_t staged;
       {
         uint32_t cnt = 0;
@@ -1097,22 +1140,23 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         load_tile (tile + 1); /* in flight during the confirmation below */
       __syncwarp ();
 
-      /* ends whose 4-byte window reaches into the carried-cursor prefix: kept unconditionally (F2 decides) */
-      if (tile == 0 && p.prefix_len) {
-        const uint64_t e = p.lead + lane;
-        const bool keep = e < min ((uint64_t)3, p.n);
-        const uint32_t m = __ballot_sync (kFull, keep);
-        if (keep)
-          cands[ncand + __popc (m & lanes_below)] = (uint32_t)e;
-        ncand += __popc (m);
-      }
+      /* appends the end s + d of every lane whose entry matched, in lane order */
+      auto append = [&] (bool ok, uint32_t rel, uint32_t ent) {
+        const uint32_t m = __ballot_sync (kFull, ok);
+        if (m) { /* rare */
+          const uint32_t at = ncand + __popc (m & lanes_below), d = ACM_S2D_DIST (ent);
+          if (ok && at < ACM_S2_CAND_CAP)
+            cands[at] = ((tile_off + rel + d) << 15) | (1u << (d >> 1));
+          ncand += __popc (m);
+        }
+      };
 
       /* ---- confirmation: up to kBatches x 32 hits in flight.  Interior tiles run straight-line code: every lane loads (idle lanes
-       * repeat the last hit) so that all text loads are issued before the first one is consumed, then all second-level loads. ---- */
+       * repeat the last hit) so that all text loads are issued before the first one is consumed, then all distance-table loads. ---- */
       auto confirm = [&] (auto nb_tag, uint32_t b) {
         constexpr int kNb = decltype (nb_tag)::value;
         uint32_t rel[kNb];
-        bool live[kNb], ok_a[kNb], ok_b[kNb];
+        bool live[kNb];
 #pragma unroll
         for (int u = 0; u < kNb; u++) {
           const uint32_t i = b + 32 * u + lane;
@@ -1121,7 +1165,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           rel[u] = ((h >> 6) << 4) + ((ti >> 3) << 9) + ((ti & 7u) << 1); /* the sampled position, tile-relative */
         }
         if (interior) {
-          uint32_t t0[kNb], t1[kNb], word[kNb];
+          uint32_t t0[kNb], t1[kNb], word[kNb], idx[kNb];
           const uint8_t *tile_m4 = text8 + tile_base - 4; /* the tile is preceded by text */
 #pragma unroll
           for (int u = 0; u < kNb; u++) { /* bytes s-3 .. s+1 from two aligned words */
@@ -1133,51 +1177,47 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           for (int u = 0; u < kNb; u++) {
             const uint32_t sh = 8u * ((rel[u] + 1u) & 3u); /* (s - 3) mod 4 = 1 or 3 */
             const uint32_t k0 = __funnelshift_r (t0[u], t1[u], sh), k1 = __funnelshift_rc (t0[u], t1[u], sh + 8u);
-            word[u] = __ldcg (p.pairbits + (((k0 >> 8) * ACM_PAIR_C0) >> pair_shift)); /* L2 only: random words must not evict the tiles from L1 */
-            t0[u] = k0 * ACM_PAIR_CA;
-            t1[u] = k1 * ACM_PAIR_CB;
+            idx[u] = ((k0 >> 8) * ACM_PAIR_C0) >> dist_shift;
+            word[u] = __ldcg (p.s2_dist + idx[u]); /* L2 only: random words must not evict the tiles from L1 */
+            t0[u] = k0 & 0xFFu; /* text[s-3] */
+            t1[u] = k1 >> 24;   /* text[s+1] */
           }
 #pragma unroll
           for (int u = 0; u < kNb; u++) {
-            ok_a[u] = live[u] && ((word[u] >> (t0[u] >> 27)) & (word[u] >> ((t0[u] >> 22) & 31u)) & 1u) != 0;
-            ok_b[u] = live[u] && ((word[u] >> (t1[u] >> 27)) & (word[u] >> ((t1[u] >> 22) & 31u)) & 1u) != 0;
+            bool more = live[u];
+            for (;;) { /* one round, except for the rare words that continue in the next one */
+              const uint32_t e0 = word[u] & 0xFFFFu, e1 = word[u] >> 16;
+              const bool ok0 = more && (e0 & ACM_S2D_VALID) && ((e0 ^ ((e0 & ACM_S2D_RIGHT) ? t1[u] : t0[u])) & 0xFFu) == 0;
+              const bool ok1 = more && (e1 & ACM_S2D_VALID) && ((e1 ^ ((e1 & ACM_S2D_RIGHT) ? t1[u] : t0[u])) & 0xFFu) == 0;
+              append (ok0, rel[u], e0);
+              append (ok1, rel[u], e1);
+              more = more && (word[u] & ACM_S2D_CONT);
+              if (!__any_sync (kFull, more))
+                break;
+              idx[u] = (idx[u] + 1u) & dist_mask;
+              word[u] = more ? __ldcg (p.s2_dist + idx[u]) : 0u;
+            }
           }
-        } else { /* first / last tile: every end is checked for its range, its window is read byte by byte */
+        } else { /* first / last tile: every window and every end is checked for its range */
+          if (lane == 0)
+            *slow_count = ncand;
+          __syncwarp ();
 #pragma unroll
-          for (int u = 0; u < kNb; u++)
-#pragma unroll
-            for (int role = 0; role < 2; role++) {
-              const uint64_t e = tile_base + rel[u] + role;
-              bool ok = live[u] && e >= first_end && e < p.n;
-              if (ok) {
-                const uint32_t win4 = (uint32_t)text8[e - 3] | ((uint32_t)text8[e - 2] << 8) | ((uint32_t)text8[e - 1] << 16) | ((uint32_t)text8[e] << 24);
-                const uint32_t word = __ldg (p.pairbits + acm_pair_word (role ? (win4 & 0xFFFFFFu) : (win4 >> 8), p.pairbits_log2));
-                const uint32_t mask = acm_pair_mask (win4, role);
-                ok = (word & mask) == mask;
-              }
-              if (role)
-                ok_b[u] = ok;
-              else
-                ok_a[u] = ok;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kNb; u++) {
-          const uint32_t ma = __ballot_sync (kFull, ok_a[u]), mb = __ballot_sync (kFull, ok_b[u]);
-          if (ma | mb) { /* rare */
-            const uint32_t na = __popc (ma);
-            if (ok_a[u]) {
-              const uint32_t at = ncand + __popc (ma & lanes_below);
-              if (at < ACM_S2_CAND_CAP)
-                cands[at] = tile_off + rel[u];
-            }
-            if (ok_b[u]) {
-              const uint32_t at = ncand + na + __popc (mb & lanes_below);
-              if (at < ACM_S2_CAND_CAP)
-                cands[at] = tile_off + rel[u] + 1u;
-            }
-            ncand += na + __popc (mb);
+          for (int u = 0; u < kNb; u++) {
+            const uint64_t s = tile_base + rel[u];
+            if (live[u] && s >= 2 && s < p.n)
+              s2_probe (p, text8, s, [&] (uint32_t d) {
+                const uint64_t e = s + d;
+                if (e >= p.lead && e < p.n) {
+                  const uint32_t at = atomicAdd (slow_count, 1u);
+                  if (at < ACM_S2_CAND_CAP)
+                    cands[at] = ((tile_off + rel[u] + d) << 15) | (1u << (d >> 1));
+                }
+              });
           }
+          __syncwarp ();
+          ncand = *slow_count;
+          __syncwarp ();
         }
       };
       {
@@ -1193,32 +1233,12 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           confirm (std::integral_constant<int, 1> (), b);
       }
       __syncwarp ();
-      if (ncand > ACM_S2_CAND_CAP) {
+      if (ncand > ACM_S2_CAND_CAP)
         hot = true;
-        ncand = 0;
-      }
-      /* the tile's survivors were appended in staging order: sort them by position (rank = number of smaller ones) */
-      const uint32_t fresh = ncand - tile_first_cand;
-      if (fresh > 1) {
-        if (fresh > 32)
-          hot = true;
-        else {
-          const uint32_t mine_pos = (uint32_t)lane < fresh ? cands[tile_first_cand + lane] : 0xFFFFFFFFu;
-          uint32_t rank = 0;
-          for (uint32_t j = 0; j < fresh; j++)
-            rank += cands[tile_first_cand + j] < mine_pos;
-          __syncwarp ();
-          if ((uint32_t)lane < fresh)
-            cands[tile_first_cand + rank] = mine_pos;
-          __syncwarp ();
-        }
-      }
-      if (hot)
-        break;
     }
 
-    /* ---- one reservation per span ---- */
-    uint64_t first = 0;
+    /* ---- the span's candidates: sorted by end position, equal ends merged (their distance masks OR-ed) ---- */
+    uint32_t nspill = 0;
     if (hot) { /* rare */
       ncand = 0;
       if (lane == 0) {
@@ -1226,7 +1246,53 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         if (at < p.hot_cap)
           p.hot_spans[at] = (uint32_t)span;
       }
+    } else if (ncand) {
+      uint32_t val[2], dm[2], rank[2] = { 0, 0 };
+      bool first[2];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const uint32_t i = lane + 32 * r;
+        first[r] = i < ncand;
+        val[r] = first[r] ? cands[i] : 0xFFFFFFFFu;
+        dm[r] = val[r] & ACM_S2_DMASK_ALL;
+      }
+      if (ncand > 1) {
+        for (uint32_t j = 0; j < ncand; j++) {
+          const uint32_t w = cands[j];
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            if ((w >> 15) == (val[r] >> 15)) {
+              dm[r] |= w & ACM_S2_DMASK_ALL;
+              if (j < (uint32_t)lane + 32 * r)
+                first[r] = false; /* an earlier entry with the same end represents it */
+            }
+        }
+        const uint32_t f0 = __ballot_sync (kFull, first[0]), f1 = __ballot_sync (kFull, first[1]);
+        for (uint32_t j = 0; j < ncand; j++)
+          if (((j < 32 ? f0 >> j : f1 >> (j - 32)) & 1u)) {
+            const uint32_t w = cands[j];
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+              rank[r] += (w >> 15) < (val[r] >> 15);
+          }
+        __syncwarp ();
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          if (first[r])
+            cands[rank[r]] = (val[r] & ~ACM_S2_DMASK_ALL) | dm[r];
+        ncand = __popc (f0) + __popc (f1);
+        __syncwarp ();
+      }
+      /* ends beyond the span (at most kS2EndSlack bytes into the next one) come last */
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const uint32_t i = lane + 32 * r;
+        nspill += __popc (__ballot_sync (kFull, i < ncand && (cands[i] >> 15) >= kS2SpanBytes));
+      }
     }
+
+    /* ---- one reservation per span ---- */
+    uint64_t first_slot = 0;
     if (ncand) {
       unsigned long long seg = 0;
       if (lane == 0)
@@ -1235,97 +1301,119 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
       if (seg + ncand > p.cand_cap) {
         if (lane == 0)
           atomicExch (p.overflow, 1u);
-        ncand = 0;
+        ncand = nspill = 0;
       } else {
-        first = seg;
+        first_slot = seg;
         const uint64_t span_base = tile0 * kTileBytes;
-        for (uint32_t i = lane; i < ncand; i += 32)
-          p.cand_pos[seg + i] = span_base + cands[i];
+        for (uint32_t i = lane; i < ncand; i += 32) {
+          const uint32_t c = cands[i];
+          p.cand_pos[seg + i] = (span_base + (c >> 15)) | ((uint64_t)(c & ACM_S2_DMASK_ALL) << 48);
+        }
       }
     }
     if (lane == 0) {
-      p.tile_first[span] = first;
+      p.tile_first[span] = first_slot;
       p.tile_n[span] = ncand;
+      p.tile_spill[span] = nspill;
     }
     __syncwarp ();
   }
 }
 
 /* F1h: the spans F1s left unfinished (more filter hits in a tile, or more candidates in the span, than its shared-memory stages
- * hold).  One warp per such span tests EVERY end position of the span exactly (4-byte window in the q-gram key set, one L2 lookup
- * per position), keeps the verdicts of the span as 1,024 ballot words in shared memory, reserves the span's segment of the candidate
- * list once and writes the positions in order -- what F1s would have produced, without its capacity limits. */
-constexpr int kHotWarps = 4;
-__global__ void __launch_bounds__ (kHotWarps * 32)
-filter_hot_spans_kernel (const __grid_constant__ FilterParams p, uint32_t nb_hot) {
-  __shared__ uint32_t s_ballots[kHotWarps][kS2SpanBytes / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t h = blockIdx.x * kHotWarps + warp;
-  if (h >= nb_hot)
-    return;
-  const uint64_t span = p.hot_spans[h], span_base = span * kS2SpanBytes;
-  const uint64_t span_end = min (p.n, span_base + kS2SpanBytes);
+ * hold).  One warp per such span probes the distance table for EVERY sampled position of the span (no filter), ORs the
+ * distance masks of the ends into a span-sized array in shared memory, reserves the span's segment of the candidate list once and
+ * writes the ends in order -- what F1s would have produced, without its capacity limits.  The grid is fixed; the number of
+ * unfinished spans is read from device memory (no host round trip between F1s and this kernel). */
+constexpr uint32_t kHotSmemBytes = (kS2SpanBytes + kS2EndSlack) * 2;
+__global__ void __launch_bounds__ (32)
+filter_hot_spans_kernel (const __grid_constant__ FilterParams p) {
+  extern __shared__ __align__ (16) unsigned char smem[];
+  uint32_t *s_mask32 = reinterpret_cast<uint32_t *> (smem); /* 16-bit distance mask per span-relative end, two per word */
+  const int lane = threadIdx.x;
+  const uint32_t nb_hot = min (*p.hot_count, p.hot_cap);
   const uint8_t *text8 = reinterpret_cast<const uint8_t *> (p.text);
-  uint32_t *ballots = s_ballots[warp];
-  uint32_t total = 0;
-  for (uint32_t w = 0; w < kS2SpanBytes / 32; w++) {
-    const uint64_t e = span_base + (uint64_t)w * 32 + lane;
-    bool ok = false;
-    if (e < span_end && e >= p.lead) {
-      if (e >= 3) {
-        const uint32_t win4 = (uint32_t)text8[e - 3] | ((uint32_t)text8[e - 2] << 8) | ((uint32_t)text8[e - 1] << 16) | ((uint32_t)text8[e] << 24);
-        ok = qset_contains (p, win4);
-      } else
-        ok = p.prefix_len != 0; /* the window reaches into the carried-cursor prefix: F2 decides */
+  constexpr uint32_t kEnds = kS2SpanBytes + kS2EndSlack;
+  for (uint32_t h = blockIdx.x; h < nb_hot; h += gridDim.x) {
+    const uint64_t span = p.hot_spans[h], span_base = span * kS2SpanBytes;
+    const uint64_t span_end = min (p.n, span_base + kS2SpanBytes);
+    for (uint32_t i = lane; i < kEnds / 2; i += 32)
+      s_mask32[i] = 0;
+    __syncwarp ();
+    auto mark = [&] (uint64_t e, uint32_t dmask) {
+      const uint32_t rel = (uint32_t)(e - span_base);
+      atomicOr (&s_mask32[rel >> 1], dmask << (16 * (rel & 1u)));
+    };
+    if (span == 0 && p.prefix_len) {
+      const uint64_t last = min ((uint64_t)(p.lmax ? p.lmax - 1 : 0), p.n);
+      for (uint64_t e = p.lead + lane; e < last && e < kEnds; e += 32)
+        mark (e, ACM_S2_DMASK_ALL);
     }
-    const uint32_t m = __ballot_sync (kFull, ok);
-    if (lane == 0)
-      ballots[w] = m;
-    total += __popc (m);
-  }
-  __syncwarp ();
-  unsigned long long seg = 0;
-  if (lane == 0 && total)
-    seg = atomicAdd (p.cand_count, (unsigned long long)total);
-  seg = __shfl_sync (kFull, seg, 0);
-  if (seg + total > p.cand_cap) {
-    if (lane == 0)
-      atomicExch (p.overflow, 1u);
-    total = 0;
-  }
-  uint64_t at = seg;
-  if (total)
-    for (uint32_t w = 0; w < kS2SpanBytes / 32; w++) {
-      const uint32_t m = ballots[w];
-      if (m >> lane & 1u)
-        p.cand_pos[at + __popc (m & ((1u << lane) - 1u))] = span_base + (uint64_t)w * 32 + lane;
-      at += __popc (m);
+    for (uint64_t s = span_base + 2 * (uint64_t)lane; s < span_end; s += 64)
+      if (s >= 2)
+        s2_probe (p, text8, s, [&] (uint32_t d) {
+          const uint64_t e = s + d;
+          if (e >= p.lead && e < p.n)
+            mark (e, 1u << (d >> 1));
+        });
+    __syncwarp ();
+    uint32_t total = 0, spill = 0;
+    for (uint32_t w = 0; w < kEnds; w += 32) {
+      const uint32_t rel = w + lane;
+      const bool on = ((s_mask32[rel >> 1] >> (16 * (rel & 1u))) & 0xFFFFu) != 0;
+      const uint32_t m = __ballot_sync (kFull, on);
+      total += __popc (m);
+      if (w >= kS2SpanBytes)
+        spill += __popc (m);
     }
-  if (lane == 0) {
-    p.tile_first[span] = seg;
-    p.tile_n[span] = total;
+    unsigned long long seg = 0;
+    if (lane == 0 && total)
+      seg = atomicAdd (p.cand_count, (unsigned long long)total);
+    seg = __shfl_sync (kFull, seg, 0);
+    if (seg + total > p.cand_cap) {
+      if (lane == 0)
+        atomicExch (p.overflow, 1u);
+      total = spill = 0;
+    }
+    uint64_t at = seg;
+    if (total)
+      for (uint32_t w = 0; w < kEnds; w += 32) {
+        const uint32_t rel = w + lane;
+        const uint32_t dmask = (s_mask32[rel >> 1] >> (16 * (rel & 1u))) & 0xFFFFu;
+        const uint32_t m = __ballot_sync (kFull, dmask != 0);
+        if (dmask)
+          p.cand_pos[at + __popc (m & ((1u << lane) - 1u))] = (span_base + rel) | ((uint64_t)dmask << 48);
+        at += __popc (m);
+      }
+    if (lane == 0) {
+      p.tile_first[span] = seg;
+      p.tile_n[span] = total;
+      p.tile_spill[span] = spill;
+    }
+    __syncwarp ();
   }
 }
 
 /* F2 / F4: one thread per candidate walks the reverse trie leftwards from the candidate's position.
  * F2 (kEmit = false) counts the keywords ending there; F3 sums the counts of each tile (its candidates are contiguous and in
  * position order); after the device scan of the tile totals, F4 (kEmit = true) walks again and writes the records of the
- * candidate at tile offset + the counts of the candidates before it in the tile, longest keyword first. */
+ * candidate at tile offset + the counts of the candidates before it in the tile, longest keyword first.
+ * The grid is fixed and the number of candidates is read from device memory: no host round trip before these kernels. */
 template <int W, bool kEmit>
 __global__ void __launch_bounds__ (256)
-filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candidates) {
-  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nb_candidates)
-    return;
-  const int64_t pos = (int64_t)p.cand_pos[c];
+filter_verify_kernel (const __grid_constant__ FilterParams p) {
+  const uint64_t nb_candidates = min ((uint64_t)*p.cand_count, p.cand_cap);
+  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nb_candidates; c += (uint64_t)gridDim.x * blockDim.x) {
+  const uint64_t packed = p.cand_pos[c];
+  const int64_t pos = (int64_t)(packed & ACM_CAND_POS_MASK);
+  const uint32_t dmask = (uint32_t)(packed >> 48); /* 0: every keyword ending here is reported */
   uint32_t expected = 0;
   uint64_t out = 0;
   if (kEmit) {
     expected = p.cand_matches[c];
     if (!expected)
-      return;
-    const uint64_t tile = (uint64_t)pos / p.tile_syms, first = 0;
-    (void)first;
+      continue;
+    const uint64_t tile = (uint64_t)pos / p.tile_syms;
     out = p.tile_offsets[tile] + p.cand_prefix[c];
     if (expected <= 2) { /* usual case: the counting pass kept them, no second walk */
       const uint4 m = p.cand_inline[c];
@@ -1336,13 +1424,18 @@ filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candid
       }
       if (out < p.capacity)
         p.matches[out] = ACMB200Match{ p.base + (uint64_t)pos, m.x, m.y };
-      return;
+      continue;
     }
   }
   uint4 first_two = make_uint4 (0, 0, 0, 0);
   uint64_t key;
   uint32_t node, kw, found = 0;
   auto report = [&] (uint32_t keyword, uint32_t len) {
+    if (dmask) { /* stride-2 candidates: only the keywords whose chosen window produced this candidate */
+      const uint32_t dd = p.kw_dist[keyword], d = (pos & 1) ? dd >> 8 : dd & 0xFFu;
+      if (!((dmask >> (d >> 1)) & 1u))
+        return;
+    }
     if (kEmit) { /* found shortest first; the record order is longest first */
       const uint64_t at = out + (expected - 1 - found);
       if (at < p.capacity)
@@ -1409,22 +1502,33 @@ filter_verify_kernel (const __grid_constant__ FilterParams p, uint64_t nb_candid
     p.cand_matches[c] = found;
     p.cand_inline[c] = first_two;
   }
+  }
 }
 
-/* F3: matches per tile = sum over the tile's candidates; also the running prefix of every candidate inside its tile. */
+/* F3: matches per tile = sum over the candidates that END in it, in end order -- its own ones (minus those the stride-2 kernel
+ * found ending in the next span) merged with the ones the previous span left for it -- and the running prefix of every such
+ * candidate, i.e. where F4 writes its records relative to the tile's offset. */
 __global__ void __launch_bounds__ (256)
 filter_tile_totals_kernel (const __grid_constant__ FilterParams p) {
   const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tile >= p.ntiles)
     return;
-  const uint32_t n = p.tile_n[tile];
-  uint32_t total = 0;
-  if (n) {
-    const uint64_t first = p.tile_first[tile];
-    for (uint32_t j = 0; j < n; j++) {
-      p.cand_prefix[first + j] = total;
-      total += p.cand_matches[first + j];
-    }
+  const uint32_t n_main = p.tile_n[tile] - (p.tile_spill ? p.tile_spill[tile] : 0u);
+  const uint64_t first = p.tile_first[tile];
+  uint32_t n_prev = 0;
+  uint64_t first_prev = 0;
+  if (p.tile_spill && tile) {
+    n_prev = p.tile_spill[tile - 1];
+    first_prev = p.tile_first[tile - 1] + p.tile_n[tile - 1] - n_prev;
+  }
+  uint32_t total = 0, i = 0, j = 0;
+  while (i < n_prev || j < n_main) {
+    bool take_prev = i < n_prev;
+    if (take_prev && j < n_main)
+      take_prev = (p.cand_pos[first_prev + i] & ACM_CAND_POS_MASK) <= (p.cand_pos[first + j] & ACM_CAND_POS_MASK);
+    const uint64_t c = take_prev ? first_prev + i++ : first + j++;
+    p.cand_prefix[c] = total;
+    total += p.cand_matches[c];
   }
   p.tile_matches[tile] = total;
 }

@@ -97,30 +97,38 @@ acm_qset_bucket (uint32_t key, uint32_t shift) {
 }
 
 /* Stride-2 filter (byte alphabets, shortest keyword >= 4): only every second text position is tested, on a 3-byte window.
- * A keyword ending at e contains the window ending at e and the one ending at e-1; exactly one of the two ends on a sampled
- * position, so every keyword puts two 3-byte keys into the shared-memory filter: its last three bytes (role A: the keyword ends ON
- * the sampled position s) and the three bytes before its last one (role B: it ends at s+1).
+ * Every keyword CHOOSES two of its own 3-byte windows, one whose last byte lies an even number of bytes before the keyword's last
+ * byte (distance dA = 0, 2, 4, ...) and one at an odd distance (dB = 1, 3, ...): whatever the parity of the position an occurrence
+ * ends on, exactly one of the two windows ends on a sampled (even) position s, and the occurrence ends at s + d.  The finalise
+ * step picks the distances greedily so that the windows' filter bits collide as much as possible (the fill of the shared-memory
+ * filter, hence its false-positive rate, falls by more than half against "always the last window"); a keyword whose proper suffix
+ * is a keyword takes that suffix's distances, so that all keywords ending on one position share them.
  * The kernel builds the 32-bit filter key with one byte permute: the three window bytes in text order, the third one repeated. */
 ACM_HD uint32_t
 acm_s2_key (uint32_t b0, uint32_t b1, uint32_t b2) {
   return b0 | (b1 << 8) | (b2 << 16) | (b2 << 24);
 }
-/* Second level, global memory (L2 resident): one 32-bit word per hashed 3-byte window; inside it two bits per (role, 4-byte
- * window ending at the candidate end position).  One word load answers "may a keyword end at s?" and "... at s+1?". */
+/* Second level, global memory (L2 resident): the distance table.  One 32-bit word per hashed 3-byte window holding two 16-bit
+ * entries {valid, right, distance d, extension byte}: "a keyword whose chosen window is this one, extended by this byte on the
+ * left (text[s-3]) or on the right (text[s+1]), ends d bytes after the window".  One word load turns a filter hit at s into the
+ * candidate end positions s + d (exact on four bytes); a word with more than two entries continues in the next word (CONT). */
 #define ACM_PAIR_C0 0x9E3779B1u
-#define ACM_PAIR_CA 0x85EBCA77u
-#define ACM_PAIR_CB 0xC2B2AE3Du
 ACM_HD uint32_t
 acm_pair_word (uint32_t gram3 /* 24 bits, first byte lowest */, uint32_t log2_words) {
   return (gram3 * ACM_PAIR_C0) >> (32 - log2_words);
 }
-ACM_HD uint32_t
-acm_pair_mask (uint32_t win4 /* the 4 bytes ending at the candidate end, last byte highest */, int role_b) {
-  const uint32_t h = win4 * (role_b ? ACM_PAIR_CB : ACM_PAIR_CA);
-  return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
-}
+#define ACM_S2D_VALID 0x8000u
+#define ACM_S2D_CONT 0x4000u  /* low entry only: more entries of this word's windows follow in the next word */
+#define ACM_S2D_RIGHT 0x2000u /* the extension byte is text[s+1]; otherwise text[s-3] */
+#define ACM_S2D_DIST(e) (((e) >> 8) & 31u)
+#define ACM_S2_DMAX 29u       /* largest distance a keyword may choose: (d >> 1) indexes the 15 bits of a candidate's distance mask */
+#define ACM_S2_DMASK_ALL 0x7FFFu
+/* A candidate of the verification kernels: end position in the low 48 bits, distance mask in the high 16 (0 = every distance).
+ * A keyword found ending there is reported only if its own chosen distance for that parity is in the mask: every occurrence is
+ * reported by exactly one candidate however many sampled windows point at its end. */
+#define ACM_CAND_POS_MASK 0xFFFFFFFFFFFFull
 #define ACM_S2_CAND_CAP 64u /* confirmed candidates a warp can hold per span */
-/* shared memory of one warp of the stride-2 kernel: staged hits (16-bit each) + the span's candidates */
+/* shared memory of one warp of the stride-2 kernel: header, staged hits (16-bit each), the span's candidates */
 #define ACM_S2_WARP_BYTES(hit_cap) (16u + (hit_cap) * 2u + ACM_S2_CAND_CAP * 4u)
 
 typedef struct {
@@ -156,8 +164,9 @@ struct acm_tables {
   uint32_t bloom_s2_words, bloom_s2_k;
   uint32_t s2_hit_cap;        /* raw filter hits a warp can stage per 2 KiB tile: 1.5 x the expected number + 32 */
   double bloom_s2_hit_rate;   /* expected fraction of sampled positions that pass (false positives + true 3-byte windows) */
-  uint32_t *pairbits;         /* second level of the stride-2 filter, 1 << pairbits_log2 words */
-  uint32_t pairbits_log2;
+  uint32_t *s2_dist;          /* second level of the stride-2 filter: the distance table, 1 << s2_dist_log2 words */
+  uint32_t s2_dist_log2;
+  uint16_t *kw_dist;          /* keyword id -> chosen distances, dA | dB << 8 */
   acm_slot *qgrams;
   uint64_t qgram_slots;       /* power of two */
   uint32_t *qset;             /* same keys as a compact set (4 keys per 16-byte bucket), widths 1 and 2 only */
