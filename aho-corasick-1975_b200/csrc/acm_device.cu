@@ -473,7 +473,6 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
   p.hot_cap = s2 ? (uint32_t)std::max<uint64_t> (p.ntiles / 8, 64) : 0; /* more unfinished spans than that: the text is dense, use the dense mode */
   p.bloom = img->d_bloom.as<uint32_t> ();
   p.bloom_words = t.bloom_words;
-  p.bloom_k = t.bloom_k;
   p.bloom2 = img->two_level ? img->d_bloom2.as<uint32_t> () : nullptr;
   p.bloom2_words = t.bloom2_words;
   p.qgrams = img->d_qgrams.as<acm_slot> ();

@@ -277,7 +277,7 @@ struct s2_build {
 
 static inline void
 s2_bits_of (uint32_t key, uint32_t words, uint32_t *word, uint32_t *b0, uint32_t *b1) {
-  const uint32_t mask = acm_bloom_mask (key, 2);
+  const uint32_t mask = acm_bloom_mask (key);
   *word = acm_bloom_word (key, words);
   *b0 = (uint32_t)__builtin_ctz (mask);
   *b1 = 31u - (uint32_t)__builtin_clz (mask); /* == b0 when both hash bits coincide */
@@ -401,8 +401,12 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
             uint8_t *chosen = &dist[2 * (size_t)r + role];
             if (*chosen != 0xFF)
               s2_apply (&b, s2_window_key (k, len, *chosen), 0);
+            /* a window at the very start of the keyword has no keyword byte before it: the distance table extends it to the
+             * RIGHT instead -- the rare case for the kernel; such a window is chosen only when the keyword has no other of this
+             * parity (4-byte keywords, odd distance) */
             uint32_t best_d = role, best = 0xFFFFFFFFu;
-            for (uint32_t d = role; d <= dmax; d += 2) {
+            const uint32_t dlast = role + 4 > len ? role : (len - 4 < dmax ? len - 4 : dmax);
+            for (uint32_t d = role; d <= dlast; d += 2) {
               const uint32_t c = s2_cost (&b, s2_window_key (k, len, d)) * 64 + d; /* ties: the window nearest to the end */
               if (c < best)
                 best = c, best_d = d;
@@ -435,10 +439,11 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
     t->kw_dist = malloc (((size_t)nk + 1) * sizeof (uint16_t));
     if (!bl || !t->s2_dist || !t->kw_dist)
       goto done;
-    for (uint32_t w = 0; w < b.words; w++)
+    for (uint32_t w = 0; w < b.words; w++) {
       for (uint32_t bit = 0; bit < 32; bit++)
         if (b.cnt[(size_t)w * 32 + bit])
           bl[w] |= 1u << bit;
+    }
     t->s2_dist_log2 = lg;
     for (uint32_t r = 0; r < nk; r++) {
       t->kw_dist[r] = (uint16_t)(dist[2 * (size_t)r] | (dist[2 * (size_t)r + 1] << 8));
@@ -457,7 +462,6 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
     t->bloom_s2 = bl;
     bl = 0;
     t->bloom_s2_words = b.words;
-    t->bloom_s2_k = 2; /* bits per key; 3 was measured slower at every filter size */
     t->bloom_s2_hit_rate = hit_rate;
     t->s2_hit_cap = hit_cap;
     break;
@@ -660,18 +664,17 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
   if (want_words < 64)
     want_words = 64;
   t->bloom_words = (uint32_t)want_words;
-  t->bloom_k = 2; /* bits per key: 3 lowers the false-positive rate but costs more than it saves */
   t->bloom = calloc (t->bloom_words, sizeof (uint32_t));
   if (!t->bloom)
     goto done;
   for (uint64_t i = 0; i < nq; i++) {
     uint32_t f = acm_fold_key (qkeys[i]);
-    t->bloom[acm_bloom_word (f, t->bloom_words)] |= acm_bloom_mask (f, t->bloom_k);
+    t->bloom[acm_bloom_word (f, t->bloom_words)] |= acm_bloom_mask (f);
   }
   double fp = 0;
   for (uint32_t i = 0; i < t->bloom_words; i++) {
     const double f = __builtin_popcount (t->bloom[i]) / 32.0;
-    fp += t->bloom_k > 2 ? f * f * f : f * f;
+    fp += f * f;
   }
   t->bloom_fp = fp / t->bloom_words;
   if (t->bloom_fp > 0.08) { /* the shared-memory level alone would flood the confirmation step: add the global level */

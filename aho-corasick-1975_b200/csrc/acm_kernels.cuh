@@ -495,7 +495,7 @@ struct FilterParams {
   uint32_t tile_syms;  /* symbols per tile */
   uint64_t ntiles;
   const uint32_t *bloom;
-  uint32_t bloom_words, bloom_k;
+  uint32_t bloom_words;
   const uint32_t *bloom2; /* optional second level in global memory */
   uint32_t bloom2_words;
   const acm_slot *qgrams;
@@ -605,8 +605,6 @@ filter_row (const uint32_t *s_bloom, uint32_t nwords, const uint32_t *__restrict
     const uint32_t lo = (uint32_t)p1, hi = (uint32_t)(p1 >> 32);
     const uint32_t word = s_bloom[__umulhi (lo, nwords)];
     uint32_t t = (word >> (hi & 31u)) & (word >> (lo & 31u));
-    if (K > 2)
-      t &= word >> (__umulhi (folded, ACM_BLOOM_C2) & 31u);
     if (kTwoLevel) { /* survivors of the shared-memory level ask the L2-resident level */
       uint32_t word2 = 0;
       if (t & 1u)
@@ -993,14 +991,15 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
   uint32_t before_tile = 0;
   /* interior: every candidate end of the tile is reportable and inside the text, every window is preceded by text */
   auto interior_tile = [&] (uint64_t t) { return t * kTileBytes >= max (p.lead, (uint64_t)4) && (t + 1) * kTileBytes + kS2EndSlack <= p.n; };
-  auto load_tile = [&] (uint64_t t) {
+  /* chained: v[] still holds tile t - 1, whose last word (lane 31's) is the word before tile t: no load for it */
+  auto load_tile = [&] (uint64_t t, bool chained) {
     const uint64_t base = t * kTileBytes;
     const uint8_t *ptr = text8 + base;
     if (base >= 4 && (t + 1) * kTileBytes <= p.n) {
+      before_tile = chained ? v[kRows - 1].w : *reinterpret_cast<const uint32_t *> (ptr - 4); /* only lane 31's copy is used */
 #pragma unroll
       for (int r = 0; r < kRows; r++) /* evict_last: the confirmation step re-reads a few words of the tile one iteration later */
         asm volatile ("ld.global.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[r].x), "=r"(v[r].y), "=r"(v[r].z), "=r"(v[r].w) : "l"(ptr + r * 512 + lane * 16));
-      before_tile = *reinterpret_cast<const uint32_t *> (ptr - 4);
     } else { /* first / last tile: bytes outside the text read as zero */
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
@@ -1025,16 +1024,20 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
   };
 
   for (;;) {
-    unsigned long long span = 0;
-    if (lane == 0)
-      span = atomicAdd (p.span_counter, 1ull);
-    span = __shfl_sync (kFull, span, 0);
-    if (span >= p.ntiles)
+    /* the next span, from the global counter; broadcast with a warp reduction (one instruction; its result is warp-uniform as
+     * far as the compiler is concerned).  The host keeps the number of spans below 2^32. */
+    uint32_t mine_span = 0;
+    if (lane == 0) {
+      const unsigned long long got = atomicAdd (p.span_counter, 1ull);
+      mine_span = got >= p.ntiles ? 0xFFFFFFFFu : (uint32_t)got;
+    }
+    const uint32_t span = __reduce_max_sync (kFull, mine_span);
+    if (span == 0xFFFFFFFFu)
       break;
-    const uint64_t tile0 = span * kSpanTiles, tile1 = min (ntiles, tile0 + kSpanTiles);
+    const uint64_t tile0 = (uint64_t)span * kSpanTiles, tile1 = min (ntiles, tile0 + kSpanTiles);
     uint32_t ncand = 0; /* warp-uniform: candidates of this span held in cands[], in no particular order until the span is done */
     bool hot = false;   /* warp-uniform: a stage of this span overflowed, the span is left to filter_hot_spans_kernel */
-    load_tile (tile0);
+    load_tile (tile0, false);
 
     /* occurrences that begin in the carried-cursor prefix end within the first lmax - 1 positions: those ends are candidates
      * for every distance (F2 decides) */
@@ -1069,17 +1072,15 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         const unsigned long long p1 = (unsigned long long)key * ACM_BLOOM_C1;
         const uint32_t lo = (uint32_t)p1, hi = (uint32_t)(p1 >> 32);
         const uint32_t word = s_bloom[__umulhi (lo, nwords)];
-        uint32_t t = (word >> (hi & 31u)) & (word >> (lo & 31u));
-        if (K > 2)
-          t &= word >> (__umulhi (key, ACM_BLOOM_C2) & 31u);
-        t &= 1u;
+        const uint32_t t = (word >> (hi & 31u)) & (word >> (lo & 31u)) & 1u;
         asm ("mad.lo.u32 %0, %0, 2, %1;" : "+r"(dst) : "r"(t)); /* dst = 2 dst + verdict on the FMA pipe (kept out of the ALU-side LOP3 trees) */
       };
 #pragma unroll
       for (int r = 0; r < kRows; r++) {
-        const uint32_t up = __shfl_up_sync (kFull, v[r].w, 1);
-        const uint32_t wrap = r == 0 ? before_tile : __shfl_sync (kFull, v[r > 0 ? r - 1 : 0].w, 31);
-        const uint32_t w[5] = { lane == 0 ? wrap : up, v[r].x, v[r].y, v[r].z, v[r].w };
+        /* the word before the lane's 16 bytes comes from the lane below; lane 0 needs the last word of the row above, which
+         * lane 31 sends in place of its own: ONE rotating shuffle per row */
+        const uint32_t send = lane == 31 ? (r == 0 ? before_tile : v[r > 0 ? r - 1 : 0].w) : v[r].w;
+        const uint32_t w[5] = { __shfl_sync (kFull, send, (lane + 31) & 31), v[r].x, v[r].y, v[r].z, v[r].w };
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           test (__byte_perm (w[j], w[j + 1], 0x4432), acc[r >> 2]); /* window ending at byte 4j of the lane's 16: two bytes of the word before */
@@ -1137,7 +1138,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         }
       }
       if (tile + 1 < tile1)
-        load_tile (tile + 1); /* in flight during the confirmation below */
+        load_tile (tile + 1, true); /* in flight during the confirmation below */
       __syncwarp ();
 
       /* appends the end s + d of every lane whose entry matched, in lane order */
@@ -1165,37 +1166,50 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
           rel[u] = ((h >> 6) << 4) + ((ti >> 3) << 9) + ((ti & 7u) << 1); /* the sampled position, tile-relative */
         }
         if (interior) {
-          uint32_t t0[kNb], t1[kNb], word[kNb], idx[kNb];
+          uint32_t t0[kNb], t1[kNb], word[kNb], key[kNb];
           const uint8_t *tile_m4 = text8 + tile_base - 4; /* the tile is preceded by text */
 #pragma unroll
-          for (int u = 0; u < kNb; u++) { /* bytes s-3 .. s+1 from two aligned words */
+          for (int u = 0; u < kNb; u++) { /* bytes s-3 .. s from two aligned words */
             const uint32_t *t32 = reinterpret_cast<const uint32_t *> (tile_m4 + (uint64_t)((rel[u] + 1u) & ~3u));
             t0[u] = t32[0]; /* through L1: the tile's lines are often still there */
             t1[u] = t32[1];
           }
 #pragma unroll
           for (int u = 0; u < kNb; u++) {
-            const uint32_t sh = 8u * ((rel[u] + 1u) & 3u); /* (s - 3) mod 4 = 1 or 3 */
-            const uint32_t k0 = __funnelshift_r (t0[u], t1[u], sh), k1 = __funnelshift_rc (t0[u], t1[u], sh + 8u);
-            idx[u] = ((k0 >> 8) * ACM_PAIR_C0) >> dist_shift;
-            word[u] = __ldcg (p.s2_dist + idx[u]); /* L2 only: random words must not evict the tiles from L1 */
-            t0[u] = k0 & 0xFFu; /* text[s-3] */
-            t1[u] = k1 >> 24;   /* text[s+1] */
+            key[u] = __funnelshift_r (t0[u], t1[u], 8u * ((rel[u] + 1u) & 3u)); /* (s - 3) mod 4 = 1 or 3 */
+            word[u] = __ldcg (p.s2_dist + (((key[u] >> 8) * ACM_PAIR_C0) >> dist_shift)); /* L2 only: random words must not evict the tiles from L1 */
           }
 #pragma unroll
           for (int u = 0; u < kNb; u++) {
-            bool more = live[u];
-            for (;;) { /* one round, except for the rare words that continue in the next one */
-              const uint32_t e0 = word[u] & 0xFFFFu, e1 = word[u] >> 16;
-              const bool ok0 = more && (e0 & ACM_S2D_VALID) && ((e0 ^ ((e0 & ACM_S2D_RIGHT) ? t1[u] : t0[u])) & 0xFFu) == 0;
-              const bool ok1 = more && (e1 & ACM_S2D_VALID) && ((e1 ^ ((e1 & ACM_S2D_RIGHT) ? t1[u] : t0[u])) & 0xFFu) == 0;
-              append (ok0, rel[u], e0);
-              append (ok1, rel[u], e1);
-              more = more && (word[u] & ACM_S2D_CONT);
-              if (!__any_sync (kFull, more))
-                break;
-              idx[u] = (idx[u] + 1u) & dist_mask;
-              word[u] = more ? __ldcg (p.s2_dist + idx[u]) : 0u;
+            /* usual entries: valid, extended to the LEFT by the window's first byte -- both halves of the word in one xor/and
+             * (VALID 0x8000 set, RIGHT 0x2000 clear, extension byte equal) */
+            const uint32_t x = (word[u] ^ ((key[u] & 0xFFu) * 0x00010001u | 0x80008000u)) & 0xA0FFA0FFu;
+            const bool ok0 = live[u] && (x & 0xFFFFu) == 0, ok1 = live[u] && (x >> 16) == 0;
+            if (__any_sync (kFull, ok0 || ok1)) { /* about one candidate per two tiles */
+              append (ok0, rel[u], word[u] & 0xFFFFu);
+              append (ok1, rel[u], word[u] >> 16);
+            }
+            /* rare: an entry extended to the RIGHT (the first window of a 4-byte keyword: VALID is bit 15 and RIGHT bit 13 of an
+             * entry) or a word that continues in the next one */
+            const bool slow = live[u] && ((word[u] & (word[u] << 2) & 0x80008000u) | (word[u] & ACM_S2D_CONT)) != 0;
+            if (__any_sync (kFull, slow)) {
+              const uint32_t left = key[u] & 0xFFu;
+              uint32_t right = 0x100u, idx = ((key[u] >> 8) * ACM_PAIR_C0) >> dist_shift, wd = word[u];
+              bool more = slow, first = true; /* the left-extended entries of the first word are done */
+              for (;;) {
+                const uint32_t e0 = wd & 0xFFFFu, e1 = wd >> 16;
+                const bool v0 = more && (e0 & ACM_S2D_VALID) && (!first || (e0 & ACM_S2D_RIGHT)), v1 = more && (e1 & ACM_S2D_VALID) && (!first || (e1 & ACM_S2D_RIGHT));
+                if (((v0 && (e0 & ACM_S2D_RIGHT)) || (v1 && (e1 & ACM_S2D_RIGHT))) && right == 0x100u)
+                  right = text8[tile_base + rel[u] + 1];
+                append (v0 && (e0 & 0xFFu) == ((e0 & ACM_S2D_RIGHT) ? right : left), rel[u], e0);
+                append (v1 && (e1 & 0xFFu) == ((e1 & ACM_S2D_RIGHT) ? right : left), rel[u], e1);
+                more = more && (wd & ACM_S2D_CONT);
+                first = false;
+                if (!__any_sync (kFull, more))
+                  break;
+                idx = (idx + 1u) & dist_mask;
+                wd = more ? __ldcg (p.s2_dist + idx) : 0u;
+              }
             }
           }
         } else { /* first / last tile: every window and every end is checked for its range */

@@ -30,14 +30,16 @@ acm_fold_key (uint64_t key) {
 }
 
 #define ACM_BLOOM_C1 0x9E3779B1u
-#define ACM_BLOOM_C2 0x85EBCA77u
-/* Blocked Bloom filter in shared memory: one 32-bit word per key, k (2 or 3) bits inside it.
+/* Blocked Bloom filter in shared memory: one 32-bit word per key, two bits inside it.
  *   p1 = folded * C1 (64-bit product): word index = mulhi (lo32 (p1), nwords)   (nwords need not be a power of two)
  *                                      bit a      = hi32 (p1) & 31              (bits 32..36 of the product: depend on every input bit)
  *                                      bit b      = lo32 (p1) & 31              (a bijection of the key's low 5 bits)
- *   k = 3 only:                        bit c      = mulhi (folded, C2) & 31
  * The bit positions sit in the low 5 bits of a register on purpose: the GPU's funnel shift takes its amount modulo 32, so the
- * kernel needs no extraction instruction, and the multiplies run on the FMA pipe next to the ALU pipe that does the shifts. */
+ * kernel needs no extraction instruction, and the multiplies run on the FMA pipe next to the ALU pipe that does the shifts.
+ * (Measured and dropped: a third bit per key -- fewer false positives do not pay for two more instructions per test; and a
+ * second bit at a FIXED distance from the first, which lets the finalise step AND the pair together and the kernel test with one
+ * shift -- 7 instead of 9 instructions per test, but the second bit then carries no information and the pass rate of the
+ * config-3 filter rose from 3.5 % to 8.9 %.) */
 ACM_HD uint32_t
 acm_mulhi32 (uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -51,12 +53,14 @@ acm_bloom_word (uint32_t folded, uint32_t nwords) {
   return acm_mulhi32 (folded * ACM_BLOOM_C1, nwords);
 }
 ACM_HD uint32_t
-acm_bloom_mask (uint32_t folded, uint32_t k) {
+acm_bloom_mask (uint32_t folded) {
   const uint32_t lo = folded * ACM_BLOOM_C1, hi = acm_mulhi32 (folded, ACM_BLOOM_C1);
-  uint32_t m = (1u << (hi & 31u)) | (1u << (lo & 31u));
-  if (k > 2)
-    m |= 1u << (acm_mulhi32 (folded, ACM_BLOOM_C2) & 31u);
-  return m;
+  return (1u << (hi & 31u)) | (1u << (lo & 31u));
+}
+ACM_HD int
+acm_bloom_test (const uint32_t *filter, uint32_t nwords, uint32_t folded) { /* what a kernel's test computes */
+  const uint32_t m = acm_bloom_mask (folded);
+  return (filter[acm_bloom_word (folded, nwords)] & m) == m;
 }
 
 /* Second-level filter for dictionaries too large for shared memory: same blocked layout, in global memory (L2 resident),
@@ -156,12 +160,12 @@ struct acm_tables {
   /* --- filter engine --- */
   uint32_t q;                 /* symbols per filter window = min(lmin, 4 for bytes / 2 otherwise) */
   uint32_t *bloom;
-  uint32_t bloom_words, bloom_k;
+  uint32_t bloom_words;
   uint32_t *bloom2;           /* optional second level in global memory (0 when the first level is selective enough) */
   uint32_t bloom2_words;
   double bloom_fp;            /* expected false-positive rate of one probe, from the actual fill of every word */
   uint32_t *bloom_s2;         /* stride-2 filter (width 1, shortest keyword >= 4): 3-byte keys, two per keyword; 0 when not applicable */
-  uint32_t bloom_s2_words, bloom_s2_k;
+  uint32_t bloom_s2_words;
   uint32_t s2_hit_cap;        /* raw filter hits a warp can stage per 2 KiB tile: 1.5 x the expected number + 32 */
   double bloom_s2_hit_rate;   /* expected fraction of sampled positions that pass (false positives + true 3-byte windows) */
   uint32_t *s2_dist;          /* second level of the stride-2 filter: the distance table, 1 << s2_dist_log2 words */

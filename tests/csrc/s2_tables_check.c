@@ -100,9 +100,8 @@ main (int argc, char **argv) {
   const uint32_t mask = (1u << t.s2_dist_log2) - 1u;
   for (uint64_t s = 2; s < n; s += 2) {
     const uint32_t key = acm_s2_key (text[s - 2], text[s - 1], text[s]);
-    const uint32_t bm = acm_bloom_mask (key, t.bloom_s2_k);
     tests++;
-    if ((t.bloom_s2[acm_bloom_word (key, t.bloom_s2_words)] & bm) != bm)
+    if (!acm_bloom_test (t.bloom_s2, t.bloom_s2_words, key))
       continue;
     hits++;
     const uint32_t gram3 = text[s - 2] | ((uint32_t)text[s - 1] << 8) | ((uint32_t)text[s] << 16);
