@@ -10,7 +10,6 @@ from .binding import (  # noqa: F401
     Machine,
     build_library,
     device_count,
-    generate_text,
     lib,
     library_path,
 )

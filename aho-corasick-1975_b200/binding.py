@@ -30,7 +30,7 @@ def build_library(quiet=True):
 class _Scan(ctypes.Structure):
     _fields_ = [("text", ctypes.c_void_p), ("nb_symbols", ctypes.c_uint64), ("lead", ctypes.c_uint64), ("base", ctypes.c_uint64),
                 ("text_on_device", ctypes.c_int), ("matches_on_device", ctypes.c_int), ("matches", ctypes.c_void_p), ("capacity", ctypes.c_uint64),
-                ("cursor", ctypes.POINTER(ctypes.c_void_p)), ("stream", ctypes.c_void_p), ("sorted", ctypes.c_int)]
+                ("cursor", ctypes.POINTER(ctypes.c_void_p)), ("stream", ctypes.c_void_p)]
 
 
 class Stats(ctypes.Structure):
@@ -40,7 +40,8 @@ class Stats(ctypes.Structure):
                 ("scan_kernel_ms", ctypes.c_double), ("main_kernel_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
                 ("last_nb_symbols", ctypes.c_uint64), ("last_nb_matches", ctypes.c_uint64), ("last_nb_candidates", ctypes.c_uint64),
                 ("main_kernel_launches", ctypes.c_uint64), ("total_kernel_launches", ctypes.c_uint64), ("fallback_count", ctypes.c_uint64), ("filter_fp", ctypes.c_double),
-                ("hot_spans", ctypes.c_uint64), ("dfa_event_scans", ctypes.c_uint64), ("filter_stride", ctypes.c_uint64)]
+                ("hot_spans", ctypes.c_uint64), ("dfa_event_scans", ctypes.c_uint64), ("filter_stride", ctypes.c_uint64),
+                ("dense_scans", ctypes.c_uint64), ("patch_count", ctypes.c_uint64), ("blob_loads", ctypes.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -69,8 +70,9 @@ def lib():
         "acm_b200_insert_keywords": (i, [vp, vp, vp, u64, vp]), "acm_b200_symbol_width": (ctypes.c_size_t, [vp]), "acm_b200_max_keyword_length": (u32, [vp]),
         "acm_b200_set_option": (i, [vp, ctypes.c_char_p, ctypes.c_char_p]), "acm_b200_get_stats": (i, [vp, ctypes.POINTER(Stats)]),
         "acm_b200_last_error": (ctypes.c_char_p, []), "acm_b200_version": (ctypes.c_char_p, []),
-        "acm_b200_generate_text": (i, [vp, i, u64, u64, i, u64, u64, u64, vp, vp, u64, vp]),
         "acm_b200_remap_text": (i, [vp, vp, ctypes.c_size_t, u64, vp]),
+        "acm_b200_keyword_order": (i, [vp, vp, u64, ctypes.POINTER(u64)]),
+        "acm_b200_save": (i, [vp, ctypes.c_char_p]), "acm_b200_load": (vp, [ctypes.c_char_p, ctypes.POINTER(i)]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -94,13 +96,37 @@ _SYM = {1: np.uint8, 2: np.uint16, 4: np.uint32}
 class Machine:
     """An ACMachine created with ACM_CMP_DEFAULT over `width`-byte letters, plus one carried scan cursor."""
 
-    def __init__(self, width=1):
+    def __init__(self, width=1, _handle=None):
         L = lib()
         self.width = width
+        if _handle is not None:  # a machine loaded from a blob: its trie is rebuilt only when somebody needs it
+            self._m = _handle
+            self._cursor = ctypes.c_void_p(None)
+            return
         self._size = ctypes.c_size_t(width)  # cmp_arg is borrowed for the machine's life (reference aho_corasick.c:147)
         cmp_default = ctypes.c_void_p.in_dll(L, "ACM_CMP_DEFAULT")
         self._m = L.acm_create(cmp_default, ctypes.addressof(self._size), None)
         self._cursor = ctypes.c_void_p(L.acm_initiate(self._m))
+
+    @classmethod
+    def load(cls, path):
+        """acm_b200_load: a machine from a blob written by save()."""
+        err = ctypes.c_int(0)
+        h = lib().acm_b200_load(os.fsencode(path), ctypes.byref(err))
+        if not h:
+            raise AcmError(err.value, f"cannot load {path}")
+        return cls(int(lib().acm_b200_symbol_width(h)), _handle=h)
+
+    def save(self, path):
+        _check(lib().acm_b200_save(self._m, os.fsencode(path)))
+
+    def keyword_order(self):
+        """Keyword ids in acm_foreach_keyword order."""
+        n = ctypes.c_uint64(0)
+        _check(lib().acm_b200_keyword_order(self._m, None, 0, ctypes.byref(n)))
+        ids = np.zeros(n.value, dtype=np.uint32)
+        _check(lib().acm_b200_keyword_order(self._m, ids.ctypes.data, len(ids), ctypes.byref(n)))
+        return ids
 
     def close(self):
         if getattr(self, "_m", None):
@@ -166,7 +192,7 @@ class Machine:
         cap = 0 if count_only else int(capacity if capacity is not None else min(max(1024, 64 * len(t)), 1 << 26))
         out = np.zeros(cap, dtype=MATCH_DTYPE)
         s = _Scan(text=t.ctypes.data if len(t) else None, nb_symbols=len(t), lead=lead, base=base, text_on_device=0, matches_on_device=0,
-                  matches=out.ctypes.data if cap else None, capacity=cap, cursor=ctypes.pointer(self._cursor) if carry else None, stream=None, sorted=1)
+                  matches=out.ctypes.data if cap else None, capacity=cap, cursor=ctypes.pointer(self._cursor) if carry else None, stream=None)
         n = ctypes.c_uint64(0)
         _check(lib().acm_b200_scan_ex(self._m, ctypes.byref(s), ctypes.byref(n)), allow_capacity=True)
         if count_only:
@@ -178,7 +204,7 @@ class Machine:
     def scan_device(self, d_text_ptr, nb_symbols, lead=0, base=0, d_matches_ptr=None, capacity=0, stream=None):
         """Device-resident text (raw pointer, 16-byte aligned); records stay on the device. Returns the total number found."""
         s = _Scan(text=d_text_ptr, nb_symbols=nb_symbols, lead=lead, base=base, text_on_device=1, matches_on_device=1, matches=d_matches_ptr, capacity=capacity,
-                  cursor=None, stream=stream, sorted=1)
+                  cursor=None, stream=stream)
         n = ctypes.c_uint64(0)
         _check(lib().acm_b200_scan_ex(self._m, ctypes.byref(s), ctypes.byref(n)), allow_capacity=True)
         return int(n.value)
@@ -186,22 +212,7 @@ class Machine:
     def scan_host_to_host(self, host_ptr, nb_symbols, out_ptr, capacity, lead=0, base=0):
         """Raw host pointers (e.g. pinned torch tensors) in and out: the end-to-end path. Returns the total number found."""
         s = _Scan(text=host_ptr, nb_symbols=nb_symbols, lead=lead, base=base, text_on_device=0, matches_on_device=0, matches=out_ptr, capacity=capacity,
-                  cursor=None, stream=None, sorted=1)
+                  cursor=None, stream=None)
         n = ctypes.c_uint64(0)
         _check(lib().acm_b200_scan_ex(self._m, ctypes.byref(s), ctypes.byref(n)), allow_capacity=True)
         return int(n.value)
-
-
-def generate_text(nb, first=0, kind=0, seed=0xC0FFEE, plant_seed=0x5EED, plant_period=0, dict_flat=None, dict_offsets=None, device_ptr=None, stream=None):
-    """Position-addressable synthetic text (DESIGN.md 'Text generator'). Host array unless device_ptr is given."""
-    L = lib()
-    nbk = 0 if dict_offsets is None else len(dict_offsets) - 1
-    df = np.ascontiguousarray(dict_flat, dtype=np.uint8) if nbk else None
-    do = np.ascontiguousarray(dict_offsets, dtype=np.uint64) if nbk else None
-    args = (first, nb, kind, seed, plant_seed, plant_period if nbk else 0, df.ctypes.data if nbk else None, do.ctypes.data if nbk else None, nbk)
-    if device_ptr is not None:
-        _check(L.acm_b200_generate_text(device_ptr, 1, *args, stream))
-        return None
-    out = np.empty(nb, dtype=np.uint8)
-    _check(L.acm_b200_generate_text(out.ctypes.data, 0, *args, None))
-    return out

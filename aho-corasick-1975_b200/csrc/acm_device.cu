@@ -81,15 +81,14 @@ struct DevBuf {
   template <typename T> T *as () const { return reinterpret_cast<T *> (ptr); }
 };
 
-struct acm_device_image {
-  int device = 0;
-  int sm_count = 0;
-  size_t smem_optin = 0;
+/* Everything ONE scan in flight needs besides the tables: streams, events, scratch buffers that grow on demand and are reused, the
+ * pinned copy of the scalars the kernels write.  A machine keeps a pool of these, so several host threads can scan one machine at
+ * the same time (the reference's scan is lock-free with a caller-owned cursor, README.md:266,364): the machine lock is held only to
+ * pick a context and to merge the statistics, never while the GPU works. */
+struct ScanContext {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[6] = {}, ev_copy[4] = {};
-  acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_s2_dist, d_kw_dist, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
-  DevBuf d_text, d_text2, d_matches, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_tile_spill, d_hot_spans, d_events, d_chunk_events, d_small;
+  DevBuf d_text, d_text2, d_matches, d_matches2, d_counts, d_offsets, d_block_sums, d_cand_pos, d_cand_matches, d_cand_prefix, d_cand_inline, d_tile_first, d_tile_n, d_tile_spill, d_hot_spans, d_events, d_chunk_events, d_small;
   struct Small { /* one pinned + one device copy of the scalars the kernels write */
     unsigned long long cand_count;
     uint64_t grand_total;
@@ -100,36 +99,93 @@ struct acm_device_image {
     uint32_t pad2;
     uint32_t prefix[1024];
   } *h_small = nullptr;
+  ACMB200Stats stats = {}; /* of the scan this context is running: merged into the machine's under the lock */
+  bool in_use = false;
+
+  int init () {
+    CUDA_TRY (cudaStreamCreateWithFlags (&stream, cudaStreamNonBlocking));
+    CUDA_TRY (cudaStreamCreateWithFlags (&copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : ev)
+      CUDA_TRY (cudaEventCreate (&e));
+    for (cudaEvent_t &e : ev_copy)
+      CUDA_TRY (cudaEventCreate (&e));
+    CUDA_TRY (cudaMallocHost (&h_small, sizeof (*h_small)));
+    return d_small.ensure (sizeof (*h_small));
+  }
+  void release () {
+    for (DevBuf *b : { &d_text, &d_text2, &d_matches, &d_matches2, &d_counts, &d_offsets, &d_block_sums, &d_cand_pos, &d_cand_matches, &d_cand_prefix, &d_cand_inline, &d_tile_first,
+                       &d_tile_n, &d_tile_spill, &d_hot_spans, &d_events, &d_chunk_events, &d_small })
+      b->release ();
+    for (cudaEvent_t e : ev)
+      if (e)
+        cudaEventDestroy (e);
+    for (cudaEvent_t e : ev_copy)
+      if (e)
+        cudaEventDestroy (e);
+    if (stream)
+      cudaStreamDestroy (stream);
+    if (copy_stream)
+      cudaStreamDestroy (copy_stream);
+    if (h_small)
+      cudaFreeHost (h_small);
+  }
+};
+
+/* The tables of one generation of the dictionary on one device.  Immutable while a scan uses it (refs > 0): a finalise that finds
+ * the dictionary changed while scans are in flight builds a new image and retires this one. */
+struct acm_device_image {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_s2_dist, d_kw_dist, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
   bool stride2 = false;   /* the stride-2 tables (bloom_s2, s2_dist, kw_dist) are resident */
   bool has_rpool = false; /* the reversed keyword pool (kw_meta, kw_rpool) is resident */
-  bool prefer_dense = false; /* the last filter scan overflowed its candidate buffers: start the next one in dense mode */
+  volatile bool prefer_dense = false; /* the last filter scan overflowed its candidate buffers: start the next one in dense mode */
+  volatile double cand_rate = -1;     /* candidates per symbol seen by the last filter scan (sizes the candidate list); < 0: none yet */
+  uint64_t generation = 0; /* of the dictionary these tables were built from */
+  int refs = 0;            /* scans in flight on this image (machine lock) */
+  std::vector<ScanContext *> contexts;
+  struct acm_device_image *retired = nullptr; /* older images still used by a scan in flight */
   ACMB200Stats stats = {};
 };
+
+static void
+free_image (acm_device_image *img) {
+  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_s2_dist, &img->d_kw_dist, &img->d_qgrams, &img->d_qset,
+                     &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool })
+    b->release ();
+  for (ScanContext *cx : img->contexts) {
+    cx->release ();
+    delete cx;
+  }
+  acm_free_tables (&img->tab);
+  delete img;
+}
 
 extern "C" void
 acm_device_release (struct acm_device_image *img) {
   if (!img)
     return;
+  int prev = -1;
+  cudaGetDevice (&prev);
   cudaSetDevice (img->device);
-  for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_s2_dist, &img->d_kw_dist, &img->d_qgrams, &img->d_qset, &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_text, &img->d_text2, &img->d_matches,
-                     &img->d_counts, &img->d_offsets, &img->d_block_sums, &img->d_cand_pos, &img->d_cand_matches, &img->d_cand_prefix, &img->d_cand_inline, &img->d_tile_first, &img->d_tile_n, &img->d_tile_spill, &img->d_hot_spans, &img->d_events, &img->d_chunk_events, &img->d_small })
-    b->release ();
-  for (cudaEvent_t e : img->ev)
-    if (e)
-      cudaEventDestroy (e);
-  for (cudaEvent_t e : img->ev_copy)
-    if (e)
-      cudaEventDestroy (e);
-  if (img->stream)
-    cudaStreamDestroy (img->stream);
-  if (img->copy_stream)
-    cudaStreamDestroy (img->copy_stream);
-  if (img->h_small)
-    cudaFreeHost (img->h_small);
-  acm_free_tables (&img->tab);
-  delete img;
+  while (img) {
+    acm_device_image *older = img->retired;
+    free_image (img);
+    img = older;
+  }
+  if (prev >= 0)
+    cudaSetDevice (prev);
 }
+
+/* restores the caller's current device when an entry point returns */
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard () { if (cudaGetDevice (&prev) != cudaSuccess) { cudaGetLastError (); prev = -1; } }
+  ~DeviceGuard () { if (prev >= 0) cudaSetDevice (prev); }
+};
 
 static int
 upload (DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
@@ -142,55 +198,11 @@ upload (DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
 }
 
 /* ---- finalise ------------------------------------------------------------------------------------------------------- */
+/* uploads the host images of img->tab and frees the big ones */
 static int
-finalise_locked (ACMachine *m, int device) {
-  if (acm_b200_device_count () <= 0)
-    return fail (ACM_B200_ERR_NO_DEVICE, "no CUDA device is available: the batch scan has no CPU fallback");
-  acm_device_image *img = m->device;
-  if (img && device >= 0 && img->device != device) {
-    acm_device_release (img);
-    img = m->device = nullptr;
-  }
-  if (!img) {
-    if (device < 0)
-      CUDA_TRY (cudaGetDevice (&device));
-    CUDA_TRY (cudaSetDevice (device));
-    img = new acm_device_image ();
-    m->device = img;
-    m->device_generation = 0;
-    img->device = device;
-    int v = 0;
-    CUDA_TRY (cudaDeviceGetAttribute (&v, cudaDevAttrMultiProcessorCount, device));
-    img->sm_count = v;
-    CUDA_TRY (cudaDeviceGetAttribute (&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    img->smem_optin = (size_t)v;
-    CUDA_TRY (cudaStreamCreateWithFlags (&img->stream, cudaStreamNonBlocking));
-    CUDA_TRY (cudaStreamCreateWithFlags (&img->copy_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t &e : img->ev)
-      CUDA_TRY (cudaEventCreate (&e));
-    for (cudaEvent_t &e : img->ev_copy)
-      CUDA_TRY (cudaEventCreate (&e));
-    CUDA_TRY (cudaMallocHost (&img->h_small, sizeof (*img->h_small)));
-    int rc = img->d_small.ensure (sizeof (*img->h_small));
-    if (rc)
-      return rc;
-  } else
-    CUDA_TRY (cudaSetDevice (img->device));
-  if (m->device_generation == m->generation)
-    return ACM_B200_OK;
-
-  const auto t0 = std::chrono::steady_clock::now ();
-  acm_free_tables (&img->tab);
-  /* shared-memory budget for the resident table: everything a block may opt in to, minus class map / staging / slack */
-  const uint64_t budget = img->smem_optin - 32 * (192 * 2 + 16) - 2048;
-  /* the stride-2 kernel works best when it leaves part of the SM's 256 KB to the L1 cache (its confirmation step re-reads text the
-   * tile loads brought in): by default it takes the 196 KB carve-out, not the largest one */
-  const uint64_t s2_smem = m->option_s2_smem_kb ? std::min<uint64_t> (img->smem_optin, m->option_s2_smem_kb * 1024 - 1024) : std::min<uint64_t> (img->smem_optin, 195 * 1024);
-  int rc = acm_build_tables (m, &img->tab, budget, m->option_no_stride2 ? 0 : s2_smem);
-  if (rc)
-    return fail (rc, "building the automaton tables failed%s", "");
+upload_tables (acm_device_image *img, cudaStream_t st, uint64_t *table_bytes) {
   acm_tables &t = img->tab;
-  cudaStream_t st = img->stream;
+  int rc;
   uint64_t bytes = 0;
   if (t.engine == ACM_B200_ENGINE_FILTER) {
     if ((rc = upload (img->d_bloom, t.bloom, (size_t)t.bloom_words * 4, st)) || (t.bloom2 && (rc = upload (img->d_bloom2, t.bloom2, (size_t)t.bloom2_words * 4, st))) || (rc = upload (img->d_qgrams, t.qgrams, t.qgram_slots * sizeof (acm_slot), st))
@@ -218,6 +230,7 @@ finalise_locked (ACMachine *m, int device) {
   free (t.bloom), t.bloom = nullptr;
   img->two_level = t.bloom2 != nullptr;
   img->prefer_dense = false;
+  img->cand_rate = -1;
   free (t.bloom2), t.bloom2 = nullptr;
   img->stride2 = t.bloom_s2 != nullptr;
   free (t.bloom_s2), t.bloom_s2 = nullptr;
@@ -232,8 +245,94 @@ finalise_locked (ACMachine *m, int device) {
   free (t.kw_meta), t.kw_meta = nullptr;
   free (t.kw_rpool), t.kw_rpool = nullptr;
   free (t.edges), t.edges = nullptr;
+  *table_bytes = bytes;
+  return ACM_B200_OK;
+}
+
+/* Machine lock held.  Leaves in m->device an image of the CURRENT dictionary on `device` (-1: the current device, or the one the
+ * machine is already on).  An image that a scan in flight is using is never touched: it is retired and a new one built. */
+static int
+finalise_locked (ACMachine *m, int device) {
+  if (acm_b200_device_count () <= 0)
+    return fail (ACM_B200_ERR_NO_DEVICE, "no CUDA device is available: the batch scan has no CPU fallback");
+  acm_device_image *img = m->device;
+  if (img && (device < 0 || img->device == device) && img->generation == m->generation) {
+    CUDA_TRY (cudaSetDevice (img->device));
+    return ACM_B200_OK;
+  }
+  if (device < 0) {
+    if (img)
+      device = img->device;
+    else
+      CUDA_TRY (cudaGetDevice (&device));
+  }
+  CUDA_TRY (cudaSetDevice (device));
+  const auto t0 = std::chrono::steady_clock::now ();
+  /* reuse the image (its device buffers) when nobody is scanning with it and it lives on the right device */
+  const bool reuse = img && img->device == device && img->refs == 0;
+  acm_device_image *fresh = reuse ? img : new acm_device_image ();
+  auto abandon = [&] (int rc) {
+    if (!reuse)
+      free_image (fresh);
+    else { /* a half-rebuilt image must not be scanned with: drop it */
+      m->device = fresh->retired;
+      fresh->retired = nullptr;
+      free_image (fresh);
+    }
+    return rc;
+  };
+  if (!reuse) {
+    fresh->device = device;
+    int v = 0;
+    if (cudaDeviceGetAttribute (&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+      return abandon (fail (ACM_B200_ERR_CUDA, "cudaDeviceGetAttribute failed%s", ""));
+    fresh->sm_count = v;
+    if (cudaDeviceGetAttribute (&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess)
+      return abandon (fail (ACM_B200_ERR_CUDA, "cudaDeviceGetAttribute failed%s", ""));
+    fresh->smem_optin = (size_t)v;
+    if (img)
+      fresh->stats = img->stats; /* counters are per machine */
+  }
+  acm_free_tables (&fresh->tab);
+  /* shared-memory budget for the resident table: everything a block may opt in to, minus class map / staging / slack */
+  const uint64_t budget = fresh->smem_optin - 32 * (192 * 2 + 16) - 2048;
+  /* the stride-2 kernel works best when it leaves part of the SM's 256 KB to the L1 cache (its confirmation step re-reads text the
+   * tile loads brought in): by default it takes the 196 KB carve-out, not the largest one */
+  const uint64_t s2_smem = m->option_no_stride2 ? 0 : (m->option_s2_smem_kb ? std::min<uint64_t> (fresh->smem_optin, m->option_s2_smem_kb * 1024 - 1024) : std::min<uint64_t> (fresh->smem_optin, 195 * 1024));
+  m->last_smem_budget = budget;
+  m->last_s2_smem = s2_smem;
+  int rc;
+  bool from_blob = false;
+  if (m->preloaded && m->preloaded_generation == m->generation && m->preloaded_budget <= budget && m->preloaded_s2_smem <= fresh->smem_optin && !m->engine_override[0]) {
+    fresh->tab = *m->preloaded; /* the images of a blob (acm_blob.c): nothing to build */
+    free (m->preloaded);
+    m->preloaded = nullptr;
+    from_blob = true;
+  } else {
+    acm_ensure_trie_locked (m);
+    if ((rc = acm_build_tables (m, &fresh->tab, budget, s2_smem)))
+      return abandon (fail (rc, "building the automaton tables failed%s", ""));
+  }
+  /* the upload runs on a stream of its own context-free: the legacy default stream of this thread */
+  uint64_t bytes = 0;
+  if ((rc = upload_tables (fresh, cudaStreamPerThread, &bytes)))
+    return abandon (rc);
+  const acm_tables &t = fresh->tab;
+  fresh->generation = m->generation;
+  if (!reuse) {
+    fresh->retired = img; /* still referenced by scans in flight (or on another device): freed when the last one ends */
+    if (img && img->refs == 0) {
+      fresh->retired = img->retired;
+      img->retired = nullptr;
+      int prev = device;
+      cudaSetDevice (img->device);
+      free_image (img);
+      cudaSetDevice (prev);
+    }
+    m->device = fresh;
+  }
   m->device_generation = m->generation;
-  ACMB200Stats &s = img->stats;
+  ACMB200Stats &s = fresh->stats;
   s.engine = t.engine;
   s.symbol_width = t.width;
   s.nb_states = t.nb_states;
@@ -242,9 +341,10 @@ finalise_locked (ACMachine *m, int device) {
   s.min_keyword_length = t.lmin;
   s.nb_classes = t.nb_classes;
   s.table_bytes = bytes;
-  s.filter_fp = t.engine == ACM_B200_ENGINE_FILTER ? (img->stride2 ? t.bloom_s2_hit_rate : t.bloom_fp) : 0;
+  s.filter_fp = t.engine == ACM_B200_ENGINE_FILTER ? (fresh->stride2 ? t.bloom_s2_hit_rate : t.bloom_fp) : 0;
   s.filter_stride = 0;
   s.finalise_count++;
+  s.blob_loads += from_blob;
   s.finalise_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count ();
   return ACM_B200_OK;
 }
@@ -253,6 +353,7 @@ extern "C" int
 acm_b200_finalise (ACMachine *m, int device) {
   if (!m)
     return fail (ACM_B200_ERR_INVALID, "null machine%s", "");
+  DeviceGuard guard;
   acm_lock (m);
   int rc = finalise_locked (m, device);
   acm_unlock (m);
@@ -292,25 +393,27 @@ extern "C" int
 acm_b200_get_stats (ACMachine *m, ACMB200Stats *stats) {
   if (!m || !stats)
     return ACM_B200_ERR_INVALID;
+  acm_lock (m);
   if (m->device)
     *stats = m->device->stats;
   else
     memset (stats, 0, sizeof (*stats));
+  acm_unlock (m);
   return ACM_B200_OK;
 }
 
 /* ---- device scan of counts ------------------------------------------------------------------------------------------ */
 static int
-device_exclusive_scan (acm_device_image *img, const uint32_t *counts, uint64_t n, uint64_t *offsets, uint64_t *d_grand, cudaStream_t st) {
+device_exclusive_scan (ScanContext *cx, const uint32_t *counts, uint64_t n, uint64_t *offsets, uint64_t *d_grand, cudaStream_t st) {
   const uint64_t nblocks = (n + kScanBlock - 1) / kScanBlock;
-  int rc = img->d_block_sums.ensure ((nblocks + 1) * 8);
+  int rc = cx->d_block_sums.ensure ((nblocks + 1) * 8);
   if (rc)
     return rc;
-  uint64_t *sums = img->d_block_sums.as<uint64_t> ();
+  uint64_t *sums = cx->d_block_sums.as<uint64_t> ();
   scan_block_sums_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>> (counts, n, sums);
   scan_spine_kernel<<<1, kScanThreads, 0, st>>> (sums, nblocks, d_grand);
   scan_apply_kernel<<<(unsigned)nblocks, kScanThreads, 0, st>>> (counts, n, sums, offsets);
-  img->stats.total_kernel_launches += 3;
+  cx->stats.total_kernel_launches += 3;
   CUDA_TRY (cudaGetLastError ());
   return ACM_B200_OK;
 }
@@ -328,7 +431,7 @@ struct ScanJob {
 /* ---- DFA pipeline --------------------------------------------------------------------------------------------------- */
 template <typename Entry, bool kShared>
 static int
-run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
   const acm_tables &t = img->tab;
   DfaParams p = {};
   p.text = reinterpret_cast<const uint8_t *> (job.d_text);
@@ -363,28 +466,28 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   const unsigned grid = (unsigned)std::min<uint64_t> ((p.nchunks + threads - 1) / threads, (uint64_t)img->sm_count * blocks_per_sm);
 
   int rc;
-  if ((rc = img->d_counts.ensure (p.nchunks * 4)) || (rc = img->d_offsets.ensure (p.nchunks * 8)))
+  if ((rc = cx->d_counts.ensure (p.nchunks * 4)) || (rc = cx->d_offsets.ensure (p.nchunks * 8)))
     return rc;
-  p.chunk_counts = img->d_counts.as<uint32_t> ();
-  p.chunk_offsets = img->d_offsets.as<uint64_t> ();
-  auto *d_small = img->d_small.as<acm_device_image::Small> ();
+  p.chunk_counts = cx->d_counts.as<uint32_t> ();
+  p.chunk_offsets = cx->d_offsets.as<uint64_t> ();
+  auto *d_small = cx->d_small.as<ScanContext::Small> ();
 
   /* pass 1 records its events when it can (shared-memory engine: 16-bit output-state index; chunk offsets of 16 bits; one event
    * slot per 4 symbols, i.e. as many bytes as the text): pass 2 then expands them instead of walking the text again */
   bool use_events = kShared && sizeof (Entry) == 2 && p.chunk <= 65536 && p.nb_out_states <= 65536 && !m->option_no_events;
   if (use_events) {
     p.events_per_chunk = (uint32_t)(p.chunk / 4);
-    if (img->d_events.ensure (p.nchunks * p.events_per_chunk * 4) || img->d_chunk_events.ensure (p.nchunks * 4)) {
+    if (cx->d_events.ensure (p.nchunks * p.events_per_chunk * 4) || cx->d_chunk_events.ensure (p.nchunks * 4)) {
       use_events = false; /* no room: walk twice */
       g_error[0] = 0;
     }
   }
   if (use_events) {
-    p.events = img->d_events.as<uint32_t> ();
-    p.chunk_events = img->d_chunk_events.as<uint32_t> ();
-    p.events_overflow = &img->d_small.as<acm_device_image::Small> ()->overflow;
-    img->h_small->overflow = 0;
-    CUDA_TRY (cudaMemcpyAsync (&img->d_small.as<acm_device_image::Small> ()->overflow, &img->h_small->overflow, 4, cudaMemcpyHostToDevice, job.st));
+    p.events = cx->d_events.as<uint32_t> ();
+    p.chunk_events = cx->d_chunk_events.as<uint32_t> ();
+    p.events_overflow = &cx->d_small.as<ScanContext::Small> ()->overflow;
+    cx->h_small->overflow = 0;
+    CUDA_TRY (cudaMemcpyAsync (&cx->d_small.as<ScanContext::Small> ()->overflow, &cx->h_small->overflow, 4, cudaMemcpyHostToDevice, job.st));
   }
   void (*count_k) (const DfaParams) = use_events ? dfa_scan_kernel<Entry, kShared, false, true> : dfa_scan_kernel<Entry, kShared, false, false>;
   /* pass 2: warp-cooperative emit when positions relative to a warp's 32 chunks fit 32 bits (always, short of absurd chunk sizes) */
@@ -393,48 +496,48 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, boo
   const size_t emit_smem = smem + (coop ? sizeof (EmitWarpState) * (threads / 32) : 0);
   CUDA_TRY (cudaFuncSetAttribute (count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)count_smem));
   CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-  img->stats.smem_bytes = emit_smem;
+  cx->stats.smem_bytes = emit_smem;
 
-  CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+  CUDA_TRY (cudaEventRecord (cx->ev[0], job.st));
   count_k<<<grid, threads, count_smem, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
-  CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
-  if ((rc = device_exclusive_scan (img, p.chunk_counts, p.nchunks, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+  CUDA_TRY (cudaEventRecord (cx->ev[1], job.st));
+  if ((rc = device_exclusive_scan (cx, p.chunk_counts, p.nchunks, cx->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
     return rc;
-  CUDA_TRY (cudaMemcpyAsync (&img->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
+  CUDA_TRY (cudaMemcpyAsync (&cx->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
   if (use_events)
-    CUDA_TRY (cudaMemcpyAsync (&img->h_small->overflow, &d_small->overflow, 4, cudaMemcpyDeviceToHost, job.st));
+    CUDA_TRY (cudaMemcpyAsync (&cx->h_small->overflow, &d_small->overflow, 4, cudaMemcpyDeviceToHost, job.st));
   CUDA_TRY (cudaStreamSynchronize (job.st));
-  *total = img->h_small->grand_total;
-  img->stats.main_kernel_launches += 1;
-  img->stats.total_kernel_launches += 1;
-  if (use_events && img->h_small->overflow)
+  *total = cx->h_small->grand_total;
+  cx->stats.main_kernel_launches += 1;
+  cx->stats.total_kernel_launches += 1;
+  if (use_events && cx->h_small->overflow)
     use_events = false; /* a chunk met more output states than it has event slots: pass 2 walks */
 
   const uint64_t want = std::min<uint64_t> (*total, job.capacity);
-  CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+  CUDA_TRY (cudaEventRecord (cx->ev[2], job.st));
   if (want) {
     if (matches_on_device)
       p.matches = user_matches;
     else {
-      if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
+      if ((rc = cx->d_matches.ensure (want * sizeof (ACMB200Match))))
         return rc;
-      p.matches = img->d_matches.as<ACMB200Match> ();
+      p.matches = cx->d_matches.as<ACMB200Match> ();
     }
     p.capacity = want;
     if (use_events)
-      img->stats.dfa_event_scans++;
+      cx->stats.dfa_event_scans++;
     if (use_events)
       dfa_emit_events_kernel<<<(unsigned)std::min<uint64_t> ((p.nchunks + 7) / 8, (uint64_t)img->sm_count * 16), 256, 0, job.st>>> (p);
     else
       emit_k<<<grid, threads, emit_smem, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
-    img->stats.main_kernel_launches += 1;
-    img->stats.total_kernel_launches += 1;
+    cx->stats.main_kernel_launches += 1;
+    cx->stats.total_kernel_launches += 1;
   }
-  CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+  CUDA_TRY (cudaEventRecord (cx->ev[3], job.st));
   job.d_matches = p.matches;
-  img->stats.last_nb_candidates = 0;
+  cx->stats.last_nb_candidates = 0;
   return ACM_B200_OK;
 }
 
@@ -447,11 +550,11 @@ enum { kFilterOverflow = 1000 }; /* internal: a candidate buffer overflowed, ret
  * scan into the library's own record buffer, which is sized from the total, synchronises before F4. */
 template <int W>
 static int
-run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool dense, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily, uint64_t *total,
-                 ACMB200Match **out_used, bool first_segment, bool last_segment) {
+run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const ScanJob &job, bool dense, uint64_t sparse_cand_cap, ACMB200Match *out, uint64_t out_cap, bool size_out_lazily,
+                 uint64_t *total, ACMB200Match **out_used, bool first_segment, bool last_segment) {
   const acm_tables &t = img->tab;
   constexpr int kRowsOpt = 4; /* rows of 512 bytes per warp tile; 2 and 8 were measured slower */
-  auto *d_small = img->d_small.as<acm_device_image::Small> ();
+  auto *d_small = cx->d_small.as<ScanContext::Small> ();
   FilterParams p = {};
   p.text = job.d_text;
   p.n = job.n;
@@ -492,9 +595,9 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
   /* stage sized for the filter's expected raw hits per tile (false positives + a margin); the dense retry takes the whole tile */
   const uint32_t expected_hits = (uint32_t)(t.bloom_fp * p.tile_syms);
   p.stage_cap = dense ? p.tile_syms : std::min<uint32_t> (p.tile_syms, std::max<uint32_t> (192, 2 * expected_hits + 128));
-  /* candidate list (32 bytes of scratch per entry): every position in dense mode; otherwise what a text as sparse in candidates as
-   * the filter assumes needs, with a wide margin -- a denser text overflows it and is redone in dense mode, segment by segment */
-  p.cand_cap = dense ? job.n : std::max<uint64_t> (job.n / (s2 ? 256 : 32), 1u << 20);
+  /* candidate list (32 bytes of scratch per entry): every position in dense mode; otherwise what the caller expects from the
+   * candidate rate it has seen (run_filter) -- a denser text overflows it and is redone with a larger list or in dense mode */
+  p.cand_cap = dense ? job.n : std::min<uint64_t> (job.n, sparse_cand_cap);
   size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
   int warps = 32;
   while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
@@ -505,19 +608,19 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
   if (smem > img->smem_optin)
     return fail (ACM_B200_ERR_NOMEM, "filter tables do not fit shared memory%s", "");
   int rc;
-  if ((rc = img->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = img->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = img->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = img->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = img->d_tile_first.ensure (p.ntiles * 8))
-      || (rc = img->d_tile_n.ensure (p.ntiles * 4)) || (rc = img->d_tile_spill.ensure (p.ntiles * 4)) || (rc = img->d_hot_spans.ensure ((size_t)p.hot_cap * 4 + 16)) || (rc = img->d_counts.ensure (p.ntiles * 4)) || (rc = img->d_offsets.ensure (p.ntiles * 8)))
+  if ((rc = cx->d_cand_pos.ensure (p.cand_cap * 8)) || (rc = cx->d_cand_matches.ensure (p.cand_cap * 4)) || (rc = cx->d_cand_prefix.ensure (p.cand_cap * 4)) || (rc = cx->d_cand_inline.ensure (p.cand_cap * 16)) || (rc = cx->d_tile_first.ensure (p.ntiles * 8))
+      || (rc = cx->d_tile_n.ensure (p.ntiles * 4)) || (rc = cx->d_tile_spill.ensure (p.ntiles * 4)) || (rc = cx->d_hot_spans.ensure ((size_t)p.hot_cap * 4 + 16)) || (rc = cx->d_counts.ensure (p.ntiles * 4)) || (rc = cx->d_offsets.ensure (p.ntiles * 8)))
     return rc;
-  p.cand_pos = img->d_cand_pos.as<uint64_t> ();
-  p.cand_matches = img->d_cand_matches.as<uint32_t> ();
-  p.cand_prefix = img->d_cand_prefix.as<uint32_t> ();
-  p.cand_inline = img->d_cand_inline.as<uint4> ();
-  p.tile_first = img->d_tile_first.as<uint64_t> ();
-  p.tile_n = img->d_tile_n.as<uint32_t> ();
-  p.tile_spill = s2 ? img->d_tile_spill.as<uint32_t> () : nullptr;
-  p.hot_spans = img->d_hot_spans.as<uint32_t> ();
-  p.tile_matches = img->d_counts.as<uint32_t> ();
-  p.tile_offsets = img->d_offsets.as<uint64_t> ();
+  p.cand_pos = cx->d_cand_pos.as<uint64_t> ();
+  p.cand_matches = cx->d_cand_matches.as<uint32_t> ();
+  p.cand_prefix = cx->d_cand_prefix.as<uint32_t> ();
+  p.cand_inline = cx->d_cand_inline.as<uint4> ();
+  p.tile_first = cx->d_tile_first.as<uint64_t> ();
+  p.tile_n = cx->d_tile_n.as<uint32_t> ();
+  p.tile_spill = s2 ? cx->d_tile_spill.as<uint32_t> () : nullptr;
+  p.hot_spans = cx->d_hot_spans.as<uint32_t> ();
+  p.tile_matches = cx->d_counts.as<uint32_t> ();
+  p.tile_offsets = cx->d_offsets.as<uint64_t> ();
   p.cand_count = &d_small->cand_count;
   p.overflow = &d_small->overflow;
 
@@ -541,43 +644,43 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
   if (!f1)
     return fail (ACM_B200_ERR_INVALID, "no filter kernel for this window length%s", "");
   CUDA_TRY (cudaFuncSetAttribute (f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  img->stats.smem_bytes = smem;
-  img->stats.filter_stride = s2 ? 2 : 1;
+  cx->stats.smem_bytes = smem;
+  cx->stats.filter_stride = s2 ? 2 : 1;
   /* header of Small (cand_count, grand_total, overflow, ...) cleared; the prefix symbols follow */
-  img->h_small->cand_count = 0;
-  img->h_small->grand_total = 0;
-  img->h_small->overflow = 0;
-  img->h_small->span_counter = 0;
-  img->h_small->hot_count = 0;
-  CUDA_TRY (cudaMemcpyAsync (d_small, img->h_small, offsetof (acm_device_image::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
+  cx->h_small->cand_count = 0;
+  cx->h_small->grand_total = 0;
+  cx->h_small->overflow = 0;
+  cx->h_small->span_counter = 0;
+  cx->h_small->hot_count = 0;
+  CUDA_TRY (cudaMemcpyAsync (d_small, cx->h_small, offsetof (ScanContext::Small, prefix) + (size_t)job.prefix_len * 4, cudaMemcpyHostToDevice, job.st));
   const unsigned grid = (unsigned)std::min<uint64_t> (((s2 ? (job.n + 2047) / 2048 : p.ntiles) + warps - 1) / warps, (uint64_t)img->sm_count);
   if (first_segment)
-    CUDA_TRY (cudaEventRecord (img->ev[0], job.st));
+    CUDA_TRY (cudaEventRecord (cx->ev[0], job.st));
   f1<<<grid, warps * 32, smem, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
   if (first_segment)
-    CUDA_TRY (cudaEventRecord (img->ev[1], job.st));
-  img->stats.main_kernel_launches += 1;
-  img->stats.total_kernel_launches += 1;
+    CUDA_TRY (cudaEventRecord (cx->ev[1], job.st));
+  cx->stats.main_kernel_launches += 1;
+  cx->stats.total_kernel_launches += 1;
   if (s2) { /* the spans whose stages overflowed are redone exactly; usually there are none and the kernel ends at once */
     CUDA_TRY (cudaFuncSetAttribute (filter_hot_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHotSmemBytes));
     filter_hot_spans_kernel<<<(unsigned)std::min<uint64_t> (p.hot_cap, (uint64_t)img->sm_count * 2), 32, kHotSmemBytes, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
-    img->stats.total_kernel_launches += 1;
+    cx->stats.total_kernel_launches += 1;
   }
   const unsigned vgrid = (unsigned)std::min<uint64_t> ((p.cand_cap + 255) / 256, (uint64_t)img->sm_count * 8), tgrid = (unsigned)((p.ntiles + 255) / 256);
   filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
   filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
-  img->stats.total_kernel_launches += 2;
-  if ((rc = device_exclusive_scan (img, p.tile_matches, p.ntiles, img->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+  cx->stats.total_kernel_launches += 2;
+  if ((rc = device_exclusive_scan (cx, p.tile_matches, p.ntiles, cx->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
     return rc;
   /* the scalars the kernels wrote: overflow flags, number of candidates / unfinished spans, grand total */
   auto fetch_small = [&] () -> int {
-    CUDA_TRY (cudaMemcpyAsync (img->h_small, d_small, offsetof (acm_device_image::Small, prefix), cudaMemcpyDeviceToHost, job.st));
+    CUDA_TRY (cudaMemcpyAsync (cx->h_small, d_small, offsetof (ScanContext::Small, prefix), cudaMemcpyDeviceToHost, job.st));
     CUDA_TRY (cudaStreamSynchronize (job.st));
-    if (img->h_small->overflow || (s2 && img->h_small->hot_count > p.hot_cap)) {
+    if (cx->h_small->overflow || (s2 && cx->h_small->hot_count > p.hot_cap)) {
       if (dense)
         return fail (ACM_B200_ERR_CUDA, "candidate buffers overflowed in dense mode%s", "");
       return kFilterOverflow;
@@ -589,67 +692,91 @@ run_filter_once (ACMachine *m, acm_device_image *img, const ScanJob &job, bool d
     p.capacity = cap;
     filter_verify_kernel<W, true><<<vgrid, 256, 0, job.st>>> (p);
     CUDA_TRY (cudaGetLastError ());
-    img->stats.total_kernel_launches += 1;
+    cx->stats.total_kernel_launches += 1;
     return ACM_B200_OK;
   };
   if (size_out_lazily) { /* single run into the library's own buffer: sized now that the total is known */
     if ((rc = fetch_small ()))
       return rc;
-    const uint64_t want = std::min<uint64_t> (img->h_small->grand_total, out_cap);
+    const uint64_t want = std::min<uint64_t> (cx->h_small->grand_total, out_cap);
     if (last_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+      CUDA_TRY (cudaEventRecord (cx->ev[2], job.st));
     if (want) {
-      if ((rc = img->d_matches.ensure (want * sizeof (ACMB200Match))))
+      if ((rc = cx->d_matches.ensure (want * sizeof (ACMB200Match))))
         return rc;
-      out = img->d_matches.as<ACMB200Match> ();
+      out = cx->d_matches.as<ACMB200Match> ();
       if ((rc = emit (want)))
         return rc;
     }
     if (last_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+      CUDA_TRY (cudaEventRecord (cx->ev[3], job.st));
   } else { /* the record buffer is known: F4 writes what fits, the host looks at the scalars once everything is queued */
     if (last_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[2], job.st));
+      CUDA_TRY (cudaEventRecord (cx->ev[2], job.st));
     if (out_cap && out && (rc = emit (out_cap)))
       return rc;
     if (last_segment)
-      CUDA_TRY (cudaEventRecord (img->ev[3], job.st));
+      CUDA_TRY (cudaEventRecord (cx->ev[3], job.st));
     if ((rc = fetch_small ()))
       return rc;
   }
-  *total = img->h_small->grand_total;
-  img->stats.last_nb_candidates += img->h_small->cand_count;
+  *total = cx->h_small->grand_total;
+  cx->stats.last_nb_candidates += cx->h_small->cand_count;
   if (s2)
-    img->stats.hot_spans += img->h_small->hot_count;
+    cx->stats.hot_spans += cx->h_small->hot_count;
   *out_used = out;
   return ACM_B200_OK;
 }
 
-/* Filter engine: one run over the whole text; if a candidate buffer overflows (text much denser in candidates than the filter's
- * false-positive rate predicts), a second attempt in dense mode, where no buffer can overflow and the text is processed in bounded
- * segments (each re-reading max depth - 1 symbols of left context) so that the scratch memory stays bounded. */
+/* Filter engine: one run over the whole text in the sparse mode, with a candidate list sized from the candidate rate seen so far
+ * (a first scan probes a prefix of the text for it: 1 Mi symbols, counted only); a list that overflows is retried once eight
+ * times larger; a text dense in candidates -- by the probe, or because the retry overflowed too -- is scanned in the dense mode,
+ * where no buffer can overflow and the text is processed in bounded segments (each re-reading max depth - 1 symbols of left
+ * context) so that the scratch memory stays bounded. */
 template <int W>
 static int
-run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
+run_filter (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uint64_t *total, bool matches_on_device, ACMB200Match *user_matches) {
   const uint64_t kDenseSegment = 64ull << 20; /* symbols */
-  img->stats.last_nb_candidates = 0;
+  const double kDenseRate = 1.0 / 64;         /* more candidates per symbol than this: the dense mode is cheaper */
+  cx->stats.last_nb_candidates = 0;
   ACMB200Match *used = nullptr;
   int rc = kFilterOverflow;
-  if (!img->prefer_dense) {
-    rc = run_filter_once<W> (m, img, job, false, user_matches, job.capacity, !matches_on_device, total, &used, true, true);
+  double rate = img->cand_rate;
+  if (rate < 0 && job.n > (8u << 20)) { /* no history: look at a prefix first */
+    ScanJob probe = job;
+    probe.n = 1u << 20;
+    probe.capacity = 0;
+    uint64_t ignored = 0;
+    rc = run_filter_once<W> (m, img, cx, probe, false, probe.n / 8, nullptr, 0, false, &ignored, &used, false, false);
+    if (rc && rc != kFilterOverflow)
+      return rc;
+    rate = rc == kFilterOverflow ? 1.0 : (double)cx->h_small->cand_count / (double)probe.n;
+    img->cand_rate = rate;
+    cx->stats.last_nb_candidates = 0;
+    rc = kFilterOverflow;
+  }
+  if (!img->prefer_dense && !(rate > kDenseRate)) {
+    uint64_t cap = std::max<uint64_t> (1u << 18, (uint64_t)((double)job.n * std::max (1.0 / 512, 2 * rate)));
+    for (int attempt = 0; attempt < 2 && rc == kFilterOverflow; attempt++, cap *= 8) {
+      cx->stats.last_nb_candidates = 0;
+      rc = run_filter_once<W> (m, img, cx, job, false, cap, user_matches, job.capacity, !matches_on_device, total, &used, true, true);
+    }
     if (rc != kFilterOverflow) {
+      if (!rc)
+        img->cand_rate = (double)cx->stats.last_nb_candidates / (double)std::max<uint64_t> (job.n, 1);
       job.d_matches = used;
       return rc;
     }
-    img->prefer_dense = true; /* texts this dense in candidates usually come in series: skip the doomed attempt next time */
-    img->stats.fallback_count++;
+    img->prefer_dense = true; /* texts this dense in candidates usually come in series: skip the doomed attempts next time */
+    cx->stats.fallback_count++;
   }
-  img->stats.last_nb_candidates = 0;
+  cx->stats.last_nb_candidates = 0;
+  cx->stats.dense_scans++;
   ACMB200Match *out = user_matches;
   if (!matches_on_device && job.capacity) {
-    if ((rc = img->d_matches.ensure (job.capacity * sizeof (ACMB200Match))))
+    if ((rc = cx->d_matches.ensure (job.capacity * sizeof (ACMB200Match))))
       return rc;
-    out = img->d_matches.as<ACMB200Match> ();
+    out = cx->d_matches.as<ACMB200Match> ();
   }
   const uint64_t seg_lead = ((uint64_t)(m->max_depth ? m->max_depth - 1 : 0) + 15) / 16 * 16;
   uint64_t produced = 0, grand = 0;
@@ -663,7 +790,7 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
     sub.prefix_len = start ? 0 : job.prefix_len;
     uint64_t seg_total = 0;
     const uint64_t room = job.capacity > produced ? job.capacity - produced : 0;
-    rc = run_filter_once<W> (m, img, sub, true, out ? out + produced : nullptr, room, false, &seg_total, &used, start == 0, start + kDenseSegment >= job.n);
+    rc = run_filter_once<W> (m, img, cx, sub, true, 0, out ? out + produced : nullptr, room, false, &seg_total, &used, start == 0, start + kDenseSegment >= job.n);
     if (rc)
       return rc;
     produced += std::min<uint64_t> (seg_total, room);
@@ -671,8 +798,10 @@ run_filter (ACMachine *m, acm_device_image *img, ScanJob &job, uint64_t *total, 
   }
   *total = grand;
   job.d_matches = out;
-  if (img->stats.last_nb_candidates < job.n / 64) /* sparse again: the next scan may use the fast mode */
+  if (cx->stats.last_nb_candidates < job.n / 64) { /* sparse again: the next scan may use the fast mode */
     img->prefer_dense = false;
+    img->cand_rate = (double)cx->stats.last_nb_candidates / (double)std::max<uint64_t> (job.n, 1);
+  }
   return ACM_B200_OK;
 }
 
@@ -707,69 +836,69 @@ advance_cursor (ACMachine *m, const ACState *from, const unsigned char *tail, ui
 }
 
 /* ---- the scan entry point -------------------------------------------------------------------------------------------- */
-extern "C" int
-acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
-  if (!m || !scan || (!scan->text && scan->nb_symbols) || (scan->capacity && !scan->matches) || scan->lead > scan->nb_symbols)
-    return fail (ACM_B200_ERR_INVALID, "invalid argument%s", "");
-  acm_lock (m);
-  int rc = finalise_locked (m, -1);
-  if (rc) {
-    acm_unlock (m);
-    return rc;
-  }
-  acm_device_image *img = m->device;
+/* counters of a finished scan into the machine's statistics (machine lock held) */
+static void
+merge_stats (ACMB200Stats &into, const ACMB200Stats &scan) {
+  into.scan_kernel_ms = scan.scan_kernel_ms;
+  into.main_kernel_ms = scan.main_kernel_ms;
+  into.h2d_ms = scan.h2d_ms;
+  into.d2h_ms = scan.d2h_ms;
+  into.last_nb_symbols = scan.last_nb_symbols;
+  into.last_nb_matches = scan.last_nb_matches;
+  into.last_nb_candidates = scan.last_nb_candidates;
+  into.smem_bytes = scan.smem_bytes;
+  into.filter_stride = scan.filter_stride;
+  into.main_kernel_launches += scan.main_kernel_launches;
+  into.total_kernel_launches += scan.total_kernel_launches;
+  into.fallback_count += scan.fallback_count;
+  into.hot_spans += scan.hot_spans;
+  into.dfa_event_scans += scan.dfa_event_scans;
+  into.dense_scans += scan.dense_scans;
+}
+
+static int
+scan_with_context (ACMachine *m, acm_device_image *img, ScanContext *cx, const ACMB200Scan *scan, uint64_t *nb_matches) {
   const acm_tables &t = img->tab;
   const size_t w = (size_t)t.width;
-  const ACState *from = scan->cursor && *scan->cursor ? *scan->cursor : m->root;
-  if (from->machine != m) {
-    acm_unlock (m);
-    return fail (ACM_B200_ERR_INVALID, "the cursor belongs to another machine%s", "");
-  }
-  cudaStream_t st = scan->stream ? (cudaStream_t)scan->stream : img->stream;
+  const ACState *from = scan->cursor && *scan->cursor ? *scan->cursor : nullptr; /* null: state 0 */
+  cudaStream_t st = scan->stream ? (cudaStream_t)scan->stream : cx->stream;
   uint64_t total = 0;
-  ACMB200Stats &stats = img->stats;
-  stats.h2d_ms = stats.d2h_ms = stats.scan_kernel_ms = stats.main_kernel_ms = 0;
-  auto finish = [&] (int code) {
-    acm_unlock (m);
-    return code;
-  };
-#define TRY_LOCKED(call)                                                                            \
-  do {                                                                                              \
-    cudaError_t e_ = (call);                                                                        \
-    if (e_ != cudaSuccess)                                                                          \
-      return finish (fail (ACM_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString (e_)));    \
-  } while (0)
+  int rc;
+  ACMB200Stats &stats = cx->stats;
+  stats = ACMB200Stats{};
 
   auto run_engine = [&] (ScanJob &job, uint64_t *tot, bool out_on_device, ACMB200Match *out) -> int {
     switch (t.engine) {
       case ACM_B200_ENGINE_DFA_SMEM:
-        return run_dfa<uint16_t, true> (m, img, job, tot, out_on_device, out);
+        return run_dfa<uint16_t, true> (m, img, cx, job, tot, out_on_device, out);
       case ACM_B200_ENGINE_DFA_GLOBAL:
-        return run_dfa<uint32_t, false> (m, img, job, tot, out_on_device, out);
+        return run_dfa<uint32_t, false> (m, img, cx, job, tot, out_on_device, out);
       default:
-        return w == 1 ? run_filter<1> (m, img, job, tot, out_on_device, out)
-                      : (w == 2 ? run_filter<2> (m, img, job, tot, out_on_device, out) : run_filter<4> (m, img, job, tot, out_on_device, out));
+        return w == 1 ? run_filter<1> (m, img, cx, job, tot, out_on_device, out)
+                      : (w == 2 ? run_filter<2> (m, img, cx, job, tot, out_on_device, out) : run_filter<4> (m, img, cx, job, tot, out_on_device, out));
     }
   };
   /* kernel times of the run that just finished (its events are recorded on st, already synchronised) */
   auto add_kernel_times = [&] () {
     float ms = 0, a = 0, b = 0;
-    cudaEventElapsedTime (&ms, img->ev[0], img->ev[3]);
+    cudaEventElapsedTime (&ms, cx->ev[0], cx->ev[3]);
     stats.scan_kernel_ms += ms;
-    cudaEventElapsedTime (&a, img->ev[0], img->ev[1]);
+    cudaEventElapsedTime (&a, cx->ev[0], cx->ev[1]);
     if (t.engine != ACM_B200_ENGINE_FILTER)
-      cudaEventElapsedTime (&b, img->ev[2], img->ev[3]);
+      cudaEventElapsedTime (&b, cx->ev[2], cx->ev[3]);
     stats.main_kernel_ms += a + b;
   };
   /* carried cursor: DFA engines start chunk 0 from its state, the filter engine sees its string as a virtual prefix */
   auto apply_cursor = [&] (ScanJob &job) -> int {
+    if (!from)
+      return ACM_B200_OK;
     if (t.engine == ACM_B200_ENGINE_FILTER) {
       if (from->depth > 1024)
         return fail (ACM_B200_ERR_INVALID, "cursor deeper than 1024 symbols%s", "");
       job.prefix_len = from->depth;
       uint32_t k = from->depth;
       for (const ACState *s = from; s->parent; s = s->parent)
-        img->h_small->prefix[--k] = acm_symbol_of_state (m, s);
+        cx->h_small->prefix[--k] = acm_symbol_of_state (m, s);
     } else
       job.init_dfa_state = t.dfa_of_state[from->id];
     return ACM_B200_OK;
@@ -786,57 +915,59 @@ acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
     job.st = st;
     if (scan->text_on_device) {
       if ((uintptr_t)scan->text & 15)
-        return finish (fail (ACM_B200_ERR_INVALID, "device text must be 16-byte aligned%s", ""));
+        return fail (ACM_B200_ERR_INVALID, "device text must be 16-byte aligned%s", "");
       job.d_text = scan->text;
     } else {
-      if ((rc = img->d_text.ensure (scan->nb_symbols * w + 64)))
-        return finish (rc);
-      TRY_LOCKED (cudaEventRecord (img->ev[4], st));
-      TRY_LOCKED (cudaMemcpyAsync (img->d_text.ptr, scan->text, scan->nb_symbols * w, cudaMemcpyHostToDevice, st));
-      TRY_LOCKED (cudaEventRecord (img->ev[5], st));
-      job.d_text = img->d_text.ptr;
+      if ((rc = cx->d_text.ensure (scan->nb_symbols * w + 64)))
+        return rc;
+      CUDA_TRY (cudaEventRecord (cx->ev[4], st));
+      CUDA_TRY (cudaMemcpyAsync (cx->d_text.ptr, scan->text, scan->nb_symbols * w, cudaMemcpyHostToDevice, st));
+      CUDA_TRY (cudaEventRecord (cx->ev[5], st));
+      job.d_text = cx->d_text.ptr;
     }
     if ((rc = apply_cursor (job)) || (rc = run_engine (job, &total, scan->matches_on_device, scan->matches)))
-      return finish (rc);
+      return rc;
     const uint64_t got = std::min<uint64_t> (total, scan->capacity);
-    TRY_LOCKED (cudaStreamSynchronize (st));
+    CUDA_TRY (cudaStreamSynchronize (st));
     if (!scan->text_on_device) {
       float ms = 0;
-      cudaEventElapsedTime (&ms, img->ev[4], img->ev[5]);
+      cudaEventElapsedTime (&ms, cx->ev[4], cx->ev[5]);
       stats.h2d_ms = ms;
     }
     add_kernel_times ();
     if (got && !scan->matches_on_device) {
       const auto c0 = std::chrono::steady_clock::now ();
-      TRY_LOCKED (cudaMemcpyAsync (scan->matches, job.d_matches, got * sizeof (ACMB200Match), cudaMemcpyDeviceToHost, st));
-      TRY_LOCKED (cudaStreamSynchronize (st));
+      CUDA_TRY (cudaMemcpyAsync (scan->matches, job.d_matches, got * sizeof (ACMB200Match), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY (cudaStreamSynchronize (st));
       stats.d2h_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - c0).count ();
     }
   } else if (scan->nb_symbols) {
     /* ---- streaming ingest of host text: the text goes through two bounded device buffers; the copy of chunk
      * i+1 (copy stream) overlaps the scan of chunk i.  Every chunk after the first is copied with max depth - 1 symbols of left
-     * context and scanned with that lead, exactly like a shard, so the records equal those of a single run. ---- */
+     * context and scanned with that lead, exactly like a shard, so the records equal those of a single run.  The records of chunk
+     * i leave on the copy stream too, from the record buffer of its parity, while chunk i+1 is scanned. ---- */
     const uint64_t chunk_syms = std::max<uint64_t> (stream_bytes / w / 4096 * 4096, 4096);
     const uint64_t seg_lead = ((uint64_t)(m->max_depth ? m->max_depth - 1 : 0) + 15) / 16 * 16;
     const unsigned char *host = reinterpret_cast<const unsigned char *> (scan->text);
-    DevBuf *bufs[2] = { &img->d_text, &img->d_text2 };
+    DevBuf *bufs[2] = { &cx->d_text, &cx->d_text2 };
     for (DevBuf *bf : bufs)
       if ((rc = bf->ensure ((chunk_syms + seg_lead) * w + 64)))
-        return finish (rc);
+        return rc;
     const uint64_t nchunks = (scan->nb_symbols + chunk_syms - 1) / chunk_syms;
     auto copy_chunk = [&] (uint64_t i) -> cudaError_t {
       const uint64_t start = i * chunk_syms, lead = i ? seg_lead : 0, len = std::min<uint64_t> (chunk_syms, scan->nb_symbols - start);
-      cudaError_t e = cudaMemcpyAsync (bufs[i & 1]->ptr, host + (start - lead) * w, (len + lead) * w, cudaMemcpyHostToDevice, img->copy_stream);
-      return e != cudaSuccess ? e : cudaEventRecord (img->ev_copy[i & 1], img->copy_stream);
+      cudaError_t e = cudaMemcpyAsync (bufs[i & 1]->ptr, host + (start - lead) * w, (len + lead) * w, cudaMemcpyHostToDevice, cx->copy_stream);
+      return e != cudaSuccess ? e : cudaEventRecord (cx->ev_copy[i & 1], cx->copy_stream);
     };
     const auto h0 = std::chrono::steady_clock::now ();
-    TRY_LOCKED (copy_chunk (0));
+    CUDA_TRY (copy_chunk (0));
     uint64_t produced = 0;
+    bool records_in_flight = false;
     for (uint64_t i = 0; i < nchunks; i++) {
       const uint64_t start = i * chunk_syms, lead = i ? seg_lead : 0, len = std::min<uint64_t> (chunk_syms, scan->nb_symbols - start);
-      TRY_LOCKED (cudaStreamWaitEvent (st, img->ev_copy[i & 1], 0));
+      CUDA_TRY (cudaStreamWaitEvent (st, cx->ev_copy[i & 1], 0));
       if (i + 1 < nchunks) /* the other buffer was last read by the scan of chunk i-1, which has completed */
-        TRY_LOCKED (copy_chunk (i + 1));
+        CUDA_TRY (copy_chunk (i + 1));
       ScanJob job = {};
       job.d_text = bufs[i & 1]->ptr;
       job.n = len + lead;
@@ -845,21 +976,33 @@ acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
       job.capacity = scan->capacity > produced ? scan->capacity - produced : 0;
       job.st = st;
       if (i == 0 && (rc = apply_cursor (job)))
-        return finish (rc);
+        return rc;
       uint64_t seg_total = 0;
-      if ((rc = run_engine (job, &seg_total, false, nullptr)))
-        return finish (rc);
-      TRY_LOCKED (cudaStreamSynchronize (st));
+      /* records of this chunk go to the record buffer of its parity: the other one may still be on its way to the host */
+      if (i & 1)
+        std::swap (cx->d_matches, cx->d_matches2);
+      rc = run_engine (job, &seg_total, false, nullptr);
+      ACMB200Match *d_records = job.d_matches;
+      if (i & 1)
+        std::swap (cx->d_matches, cx->d_matches2);
+      if (rc)
+        return rc;
+      CUDA_TRY (cudaStreamSynchronize (st));
       add_kernel_times ();
       const uint64_t got = std::min<uint64_t> (seg_total, job.capacity);
-      if (got) {
-        TRY_LOCKED (cudaMemcpyAsync (scan->matches + produced, job.d_matches, got * sizeof (ACMB200Match),
-                                     scan->matches_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        TRY_LOCKED (cudaStreamSynchronize (st));
+      if (got) { /* on the copy stream, behind the text copy of chunk i+1: the scan of chunk i+1 does not wait for it */
+        CUDA_TRY (cudaMemcpyAsync (scan->matches + produced, d_records, got * sizeof (ACMB200Match), scan->matches_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                   cx->copy_stream));
+        CUDA_TRY (cudaEventRecord (cx->ev_copy[2 + (i & 1)], cx->copy_stream));
+        records_in_flight = true;
       }
+      /* the record buffer of the NEXT chunk's parity must have left before that chunk's emit kernel writes it */
+      if (i >= 1 && records_in_flight)
+        CUDA_TRY (cudaStreamWaitEvent (st, cx->ev_copy[2 + ((i + 1) & 1)], 0));
       produced += got;
       total += seg_total;
     }
+    CUDA_TRY (cudaStreamSynchronize (cx->copy_stream));
     stats.h2d_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - h0).count (); /* whole pipeline, copies overlapped */
   }
   /* cursor out */
@@ -868,17 +1011,75 @@ acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
     std::vector<unsigned char> buf (tail * w + 1);
     const unsigned char *src = reinterpret_cast<const unsigned char *> (scan->text) + (scan->nb_symbols - tail) * w;
     if (scan->text_on_device) {
-      TRY_LOCKED (cudaMemcpy (buf.data (), src, tail * w, cudaMemcpyDeviceToHost));
+      CUDA_TRY (cudaMemcpy (buf.data (), src, tail * w, cudaMemcpyDeviceToHost));
       src = buf.data ();
     }
-    *scan->cursor = advance_cursor (m, from, src, tail, scan->nb_symbols < m->max_depth);
+    *scan->cursor = advance_cursor (m, from ? from : m->root, src, tail, scan->nb_symbols < m->max_depth);
   }
   stats.last_nb_symbols = scan->nb_symbols;
   stats.last_nb_matches = total;
   if (nb_matches)
     *nb_matches = total;
-  acm_unlock (m);
   return total > scan->capacity && scan->capacity ? ACM_B200_ERR_CAPACITY : ACM_B200_OK;
+}
+
+extern "C" int
+acm_b200_scan_ex (ACMachine *m, const ACMB200Scan *scan, uint64_t *nb_matches) {
+  if (!m || !scan || (!scan->text && scan->nb_symbols) || (scan->capacity && !scan->matches) || scan->lead > scan->nb_symbols)
+    return fail (ACM_B200_ERR_INVALID, "invalid argument%s", "");
+  DeviceGuard guard;
+  if (scan->cursor) /* a carried cursor lives in the keyword trie */
+    acm_ensure_trie (m);
+  if (scan->cursor && *scan->cursor && (*scan->cursor)->machine != m)
+    return fail (ACM_B200_ERR_INVALID, "the cursor belongs to another machine%s", "");
+  /* machine lock: tables up to date, an image reference and a scan context of our own; then the GPU works without it */
+  acm_lock (m);
+  int rc = finalise_locked (m, -1);
+  if (rc) {
+    acm_unlock (m);
+    return rc;
+  }
+  acm_device_image *img = m->device;
+  ScanContext *cx = nullptr;
+  for (ScanContext *c : img->contexts)
+    if (!c->in_use) {
+      cx = c;
+      break;
+    }
+  if (!cx) {
+    cx = new ScanContext ();
+    if ((rc = cx->init ())) {
+      cx->release ();
+      delete cx;
+      acm_unlock (m);
+      return rc;
+    }
+    img->contexts.push_back (cx);
+  }
+  cx->in_use = true;
+  img->refs++;
+  acm_unlock (m);
+
+  rc = scan_with_context (m, img, cx, scan, nb_matches);
+  if (rc == ACM_B200_ERR_CUDA)
+    cudaStreamSynchronize (cx->stream); /* leave nothing of a failed scan in flight on the context */
+
+  acm_lock (m);
+  cx->in_use = false;
+  img->refs--;
+  merge_stats (m->device->stats, cx->stats);
+  if (img != m->device && img->refs == 0) { /* retired while we were scanning: we were its last user */
+    for (acm_device_image *p = m->device; p; p = p->retired)
+      if (p->retired == img) {
+        p->retired = img->retired;
+        img->retired = nullptr;
+        cudaSetDevice (img->device);
+        free_image (img);
+        break;
+      }
+  }
+  acm_unlock (m);
+  return rc;
 }
 
 extern "C" int
@@ -889,56 +1090,5 @@ acm_b200_scan (ACMachine *m, const ACState **cursor, const void *text, uint64_t 
   s.matches = matches;
   s.capacity = capacity;
   s.cursor = cursor;
-  s.sorted = 1;
   return acm_b200_scan_ex (m, &s, nb_matches);
-}
-
-/* ---- synthetic text --------------------------------------------------------------------------------------------------- */
-extern "C" int
-acm_b200_generate_text (void *dst, int dst_on_device, uint64_t first, uint64_t nb, int kind, uint64_t seed, uint64_t plant_seed, uint64_t plant_period,
-                        const uint8_t *dict_symbols, const uint64_t *dict_offsets, uint64_t dict_nb, void *stream) {
-  if (!dst && nb)
-    return fail (ACM_B200_ERR_INVALID, "null destination%s", "");
-  GenParams g = {};
-  g.dst = reinterpret_cast<uint8_t *> (dst);
-  g.first = first;
-  g.nb = nb;
-  g.kind = kind;
-  g.seed = seed;
-  g.plant_seed = plant_seed;
-  g.plant_period = plant_period;
-  g.dict_nb = plant_period ? dict_nb : 0;
-  if (!dst_on_device) {
-    g.dict_symbols = dict_symbols;
-    g.dict_offsets = dict_offsets;
-    for (uint64_t i = 0; i < nb; i++)
-      g.dst[i] = gen_byte (g, first + i);
-    return ACM_B200_OK;
-  }
-  if (acm_b200_device_count () <= 0)
-    return fail (ACM_B200_ERR_NO_DEVICE, "no CUDA device%s", "");
-  if ((uintptr_t)dst & 15)
-    return fail (ACM_B200_ERR_INVALID, "device destination must be 16-byte aligned%s", "");
-  cudaStream_t st = (cudaStream_t)stream;
-  void *d_sym = nullptr, *d_off = nullptr;
-  if (g.dict_nb) {
-    const size_t sym_bytes = dict_offsets[dict_nb], off_bytes = (dict_nb + 1) * 8;
-    CUDA_TRY (cudaMalloc (&d_sym, sym_bytes ? sym_bytes : 1));
-    CUDA_TRY (cudaMalloc (&d_off, off_bytes));
-    CUDA_TRY (cudaMemcpyAsync (d_sym, dict_symbols, sym_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_TRY (cudaMemcpyAsync (d_off, dict_offsets, off_bytes, cudaMemcpyHostToDevice, st));
-    g.dict_symbols = reinterpret_cast<const uint8_t *> (d_sym);
-    g.dict_offsets = reinterpret_cast<const uint64_t *> (d_off);
-  }
-  int sms = 148, dev = 0;
-  cudaGetDevice (&dev);
-  cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
-  generate_text_kernel<<<sms * 8, 256, 0, st>>> (g);
-  CUDA_TRY (cudaGetLastError ());
-  CUDA_TRY (cudaStreamSynchronize (st));
-  if (d_sym)
-    cudaFree (d_sym);
-  if (d_off)
-    cudaFree (d_off);
-  return ACM_B200_OK;
 }

@@ -293,6 +293,12 @@ acm_release (ACMachine *m) {
     m->arena = a->next;
     free (a);
   }
+  free (m->lazy_symbols);
+  free (m->lazy_offsets);
+  if (m->preloaded) {
+    acm_free_tables (m->preloaded);
+    free (m->preloaded);
+  }
   free (m->keywords);
   free (m->scratch);
   free (m->class_letter);
@@ -306,15 +312,14 @@ acm_release (ACMachine *m) {
 ACState *
 acm_initiate (ACMachine *m) {
   REQUIRE (m, "Invalid null machine.");
+  acm_ensure_trie (m);
   return m->root;
 }
 
 /* ---- public: dictionary ------------------------------------------------------------------------------------------- */
-void
-acm_insert_letter_of_keyword (ACState **state, void *letter) {
-  REQUIRE (state && *state && letter, "Invalid null state or letter.");
-  struct _ac_machine *m = (*state)->machine;
-  acm_lock (m);
+/* insertion of one letter with the machine lock held */
+static void
+insert_letter_locked (struct _ac_machine *m, ACState **state, void *letter) {
   int64_t k = child_slot (*state, letter);
   if (k >= 0) {
     *state = (*state)->children[k];
@@ -322,6 +327,14 @@ acm_insert_letter_of_keyword (ACState **state, void *letter) {
       m->dtor (letter); /* the edge keeps its first letter; the duplicate is handed back at once */
   } else
     *state = enter_child (*state, letter, (uint32_t)~k);
+}
+
+void
+acm_insert_letter_of_keyword (ACState **state, void *letter) {
+  REQUIRE (state && *state && letter, "Invalid null state or letter.");
+  struct _ac_machine *m = (*state)->machine;
+  acm_lock (m);
+  insert_letter_locked (m, state, letter);
   acm_unlock (m);
 }
 
@@ -338,16 +351,10 @@ count_new_output (struct _ac_machine *m, struct _ac_state *n) {
   }
 }
 
-void *
-acm_insert_end_of_keyword (ACState **state, void *value, void (*dtor) (void *)) {
-  REQUIRE (state && *state, "Invalid null state.");
+/* end of a keyword with the machine lock held; *state must not be state 0 */
+static void *
+insert_end_locked (struct _ac_machine *m, ACState **state, void *value, void (*dtor) (void *)) {
   struct _ac_state *s = *state;
-  struct _ac_machine *m = s->machine;
-  acm_lock (m);
-  if (!s->parent) {
-    acm_unlock (m); /* do not die holding the lock */
-    acm_fatal (__func__, "acm_insert_letter_of_keyword should be called first.");
-  }
   if (s->rank == ACM_NONE) {
     if (m->nb_sequences == m->cap_keywords) {
       size_t cap = m->cap_keywords ? m->cap_keywords * 2 : 64;
@@ -372,6 +379,19 @@ acm_insert_end_of_keyword (ACState **state, void *value, void (*dtor) (void *)) 
     s->value_dtor = dtor;
   }
   *state = m->root;
+  return previous;
+}
+
+void *
+acm_insert_end_of_keyword (ACState **state, void *value, void (*dtor) (void *)) {
+  REQUIRE (state && *state, "Invalid null state.");
+  struct _ac_machine *m = (*state)->machine;
+  acm_lock (m);
+  if (!(*state)->parent) {
+    acm_unlock (m); /* do not die holding the lock */
+    acm_fatal (__func__, "acm_insert_letter_of_keyword should be called first.");
+  }
+  void *previous = insert_end_locked (m, state, value, dtor);
   acm_unlock (m);
   return previous;
 }
@@ -379,7 +399,7 @@ acm_insert_end_of_keyword (ACState **state, void *value, void (*dtor) (void *)) 
 size_t
 acm_nb_keywords (const ACMachine *m) {
   REQUIRE (m, "Invalid null machine.");
-  return m->nb_sequences;
+  return m->lazy_symbols ? (size_t)m->lazy_nb : m->nb_sequences;
 }
 
 /* ---- public: per-symbol scan -------------------------------------------------------------------------------------- */
@@ -432,13 +452,18 @@ acm_get_match (const ACState *state, size_t index, MatchHolder *matcher) {
 
 int
 acm_b200_keyword (const ACMachine *m, uint32_t keyword, MatchHolder *holder) {
-  if (!m || !holder || keyword >= m->nb_sequences)
+  if (!m || !holder)
+    return ACM_B200_ERR_INVALID;
+  acm_ensure_trie ((ACMachine *)m);
+  if (keyword >= m->nb_sequences)
     return ACM_B200_ERR_INVALID;
   fill_holder (m->keywords[keyword], holder);
   return ACM_B200_OK;
 }
 
 /* ---- public: introspection ---------------------------------------------------------------------------------------- */
+static int acm_walk_keywords (const ACMachine *m, void (*op) (MatchHolder), uint32_t *ids, uint64_t capacity, uint64_t *nb);
+
 struct walk_frame {
   const struct _ac_state *state;
   uint32_t next_child;
@@ -449,16 +474,38 @@ acm_foreach_keyword (const ACMachine *m, void (*op) (MatchHolder)) {
   REQUIRE (m, "Invalid null machine.");
   if (!op)
     return;
+  acm_ensure_trie ((ACMachine *)m);
+  acm_walk_keywords (m, op, 0, 0, 0);
+}
+
+/* keyword ids in the order acm_foreach_keyword visits the keywords (reference aho_corasick.c:490-531: pre-order, children in
+ * comparator order): ids[k] = id of the k-th keyword the callback would receive.  *nb receives the number of keywords. */
+int
+acm_b200_keyword_order (const ACMachine *m, uint32_t *ids, uint64_t capacity, uint64_t *nb) {
+  if (!m || (capacity && !ids))
+    return ACM_B200_ERR_INVALID;
+  acm_ensure_trie ((ACMachine *)m);
+  return acm_walk_keywords (m, 0, ids, capacity, nb);
+}
+
+static int
+acm_walk_keywords (const ACMachine *m, void (*op) (MatchHolder), uint32_t *ids, uint64_t capacity, uint64_t *nb) {
   /* pre-order, children in comparator order (reference aho_corasick.c:512-531) */
   size_t cap = (size_t)m->lmax + 2, top = 0;
+  uint64_t seen = 0;
   struct walk_frame *stack = malloc (cap * sizeof (*stack));
   const void **letters = malloc (cap * sizeof (*letters));
   REQUIRE (stack && letters, "Out of memory.");
   stack[top++] = (struct walk_frame){ m->root, 0 };
   while (top) {
     struct walk_frame *f = &stack[top - 1];
-    if (f->next_child == 0 && f->state->rank != ACM_NONE)
-      op ((MatchHolder){ .letters = letters, .length = f->state->depth, .value = f->state->value });
+    if (f->next_child == 0 && f->state->rank != ACM_NONE) {
+      if (op)
+        op ((MatchHolder){ .letters = letters, .length = f->state->depth, .value = f->state->value });
+      if (seen < capacity)
+        ids[seen] = f->state->rank;
+      seen++;
+    }
     if (f->next_child < f->state->nb_children) {
       const struct _ac_state *c = f->state->children[f->next_child++];
       if (c->depth + 1 >= cap) { /* keywords longer than lmax may be under construction */
@@ -474,6 +521,9 @@ acm_foreach_keyword (const ACMachine *m, void (*op) (MatchHolder)) {
   }
   free (stack);
   free (letters);
+  if (nb)
+    *nb = seen;
+  return seen > capacity && capacity ? ACM_B200_ERR_CAPACITY : ACM_B200_OK;
 }
 
 /* Debug dump, same layout as the reference's (aho_corasick.c:533-594): one line per branch,
@@ -515,6 +565,7 @@ acm_print (ACMachine *m, FILE *stream, PRINT_TYPE printer) {
   REQUIRE (m, "Invalid null machine.");
   if (!stream)
     return;
+  acm_ensure_trie (m);
   int column = 0;
   fprintf (stream, "\n");
   print_branches (m->root, stream, &column, 0, printer);
@@ -538,17 +589,11 @@ acm_b200_max_keyword_length (const ACMachine *m) {
  * of acm_b200_symbol_width() bytes.  The letters are copied into storage owned by the machine (the per-letter API keeps the
  * caller's pointers, reference aho_corasick.c:248).  Only for machines created without a letter destructor.  ids[k] (optional)
  * receives the keyword id, an existing id for a duplicate. */
-int
-acm_b200_insert_keywords (ACMachine *m, const void *symbols, const uint64_t *offsets, uint64_t nb, uint32_t *ids) {
-  if (!m || !offsets || (!symbols && nb && offsets[nb]) || m->dtor)
-    return ACM_B200_ERR_INVALID;
-  if (m->symbol_kind != ACM_SYM_RAW1 && m->symbol_kind != ACM_SYM_RAW2 && m->symbol_kind != ACM_SYM_RAW4)
-    return ACM_B200_ERR_ALPHABET;
+static int
+insert_packed_locked (ACMachine *m, const void *symbols, const uint64_t *offsets, uint64_t nb, uint32_t *ids) {
   const size_t w = m->symbol_size;
-  acm_lock (m);
   const int bulk = nb >= 256; /* below that the incremental maintenance is cheaper than a full pass */
   m->bulk = bulk;
-  acm_unlock (m);
   int rc = ACM_B200_OK;
   for (uint64_t k = 0; k < nb && rc == ACM_B200_OK; k++) {
     const size_t len = (size_t)(offsets[k + 1] - offsets[k]), bytes = (len * w + 7) & ~(size_t)7;
@@ -573,19 +618,63 @@ acm_b200_insert_keywords (ACMachine *m, const void *symbols, const uint64_t *off
     ACState *s = m->root;
     const size_t states_before = m->nb_states;
     for (size_t i = 0; i < len; i++)
-      acm_insert_letter_of_keyword (&s, copy + i * w);
+      insert_letter_locked (m, &s, copy + i * w);
     if (m->nb_states != states_before)
       m->arena->used += bytes; /* at least one letter pointer was kept */
     const uint32_t id = s->rank != ACM_NONE ? s->rank : (uint32_t)m->nb_sequences;
-    acm_insert_end_of_keyword (&s, 0, 0);
+    insert_end_locked (m, &s, 0, 0);
     if (ids)
       ids[k] = id;
   }
-  if (bulk) {
-    acm_lock (m);
+  if (bulk) { /* the states inserted above have no links yet: nobody else sees them, the lock is still held */
     m->bulk = 0;
     rebuild_links (m);
-    acm_unlock (m);
   }
   return rc;
+}
+
+int
+acm_b200_insert_keywords (ACMachine *m, const void *symbols, const uint64_t *offsets, uint64_t nb, uint32_t *ids) {
+  if (!m || !offsets || (!symbols && nb && offsets[nb]) || m->dtor)
+    return ACM_B200_ERR_INVALID;
+  if (m->symbol_kind != ACM_SYM_RAW1 && m->symbol_kind != ACM_SYM_RAW2 && m->symbol_kind != ACM_SYM_RAW4)
+    return ACM_B200_ERR_ALPHABET;
+  acm_ensure_trie (m);
+  acm_lock (m); /* held for the whole load: a scan or an insertion on another thread never sees a state without its links */
+  const int rc = insert_packed_locked (m, symbols, offsets, nb, ids);
+  acm_unlock (m);
+  return rc;
+}
+
+/* A machine loaded from a blob (acm_blob.c) keeps its dictionary packed until somebody needs the trie: the per-symbol API, a
+ * carried cursor, an insertion, the keyword enumeration.  The batch scan itself only needs the tables of the blob. */
+void
+acm_ensure_trie_locked (ACMachine *m) {
+  if (!m->lazy_symbols)
+    return;
+  void *symbols = m->lazy_symbols;
+  uint64_t *offsets = m->lazy_offsets;
+  const uint64_t generation = m->generation;
+  const int rc = insert_packed_locked (m, symbols, offsets, m->lazy_nb, 0); /* rank order: every keyword gets its id back */
+  REQUIRE (rc == ACM_B200_OK && m->nb_sequences == m->lazy_nb, "The packed dictionary of the blob is inconsistent.");
+  m->lazy_symbols = 0;
+  m->lazy_offsets = 0;
+  free (symbols);
+  free (offsets);
+  /* same dictionary, same tables -- except the state-id map of the DFA engines (ids are creation order), which a carried
+   * cursor needs: those tables are rebuilt at the next scan */
+  m->generation = m->lazy_tables_use_state_ids ? generation + 1 : generation;
+  if (!m->lazy_tables_use_state_ids) {
+    if (m->preloaded)
+      m->preloaded_generation = m->generation;
+  }
+}
+
+void
+acm_ensure_trie (ACMachine *m) {
+  if (!m->lazy_symbols)
+    return;
+  acm_lock (m);
+  acm_ensure_trie_locked (m);
+  acm_unlock (m);
 }

@@ -82,6 +82,15 @@ struct _ac_machine {
   size_t class_states_done, cap_class_states;
   int bulk; /* set while acm_b200_insert_keywords loads many keywords: links are rebuilt by one BFS at the end */
   struct acm_arena *arena; /* letters copied by acm_b200_insert_keywords */
+  /* a machine loaded from a blob (acm_blob.c): dictionary still packed (rank order), tables ready for upload */
+  void *lazy_symbols;
+  uint64_t *lazy_offsets;
+  uint64_t lazy_nb;
+  int lazy_tables_use_state_ids; /* the preloaded tables belong to a DFA engine (their cursor map is keyed by state id) */
+  size_t owned_symbol_size;      /* cmp_arg of such a machine */
+  struct acm_tables *preloaded;  /* tables of the blob, valid while generation == preloaded_generation */
+  uint64_t preloaded_generation, preloaded_budget, preloaded_s2_smem;
+  uint64_t last_smem_budget, last_s2_smem; /* shared-memory sizes of the last finalise (what acm_b200_save builds for) */
   /* GPU side */
   struct acm_device_image *device;
   uint64_t device_generation;
@@ -89,6 +98,7 @@ struct _ac_machine {
   uint64_t option_bloom_words, option_threads, option_stream_bytes;
   int option_no_stride2, option_no_events;
   uint64_t option_s2_smem_kb, option_s2_batches;
+  int option_no_patch; /* 0: tables are patched in place after append-only insertions where possible */
 };
 
 /* acm_host.c */
@@ -97,6 +107,10 @@ void acm_lock (struct _ac_machine *m);
 void acm_unlock (struct _ac_machine *m);
 const struct _ac_state *acm_host_goto (const struct _ac_state *s, const void *letter);
 struct _ac_state *acm_find_child (const struct _ac_state *s, const void *letter);
+void acm_ensure_trie (struct _ac_machine *m);
+void acm_ensure_trie_locked (struct _ac_machine *m); /* machine lock held */
+struct acm_tables;
+void acm_free_tables (struct acm_tables *t);
 
 /* acm_device.cu */
 void acm_device_release (struct acm_device_image *image);

@@ -1547,61 +1547,4 @@ filter_tile_totals_kernel (const __grid_constant__ FilterParams p) {
   p.tile_matches[tile] = total;
 }
 
-/* ------------------------------------------------------------------------------------------------------------------ */
-/* Position-addressable synthetic text (bench / test support)                                                          */
-/* ------------------------------------------------------------------------------------------------------------------ */
-struct GenParams {
-  uint8_t *dst;
-  uint64_t first, nb;
-  int kind;
-  uint64_t seed, plant_seed, plant_period;
-  const uint8_t *dict_symbols;
-  const uint64_t *dict_offsets;
-  uint64_t dict_nb;
-};
-
-ACM_HD uint64_t
-gen_raw64 (uint64_t seed, uint64_t k) {
-  return acm_mix64 (seed + k * 0x9E3779B97F4A7C15ull);
-}
-
-/* byte at absolute position i; identical on host and device */
-ACM_HD uint8_t
-gen_byte (const GenParams &g, uint64_t i) {
-  if (g.plant_period && g.dict_nb) {
-    /* one keyword per period; it may spill into the next period, where the next period's own plant wins */
-    const uint64_t blk = i / g.plant_period, off = i % g.plant_period;
-    for (int back = 0; back < 2; back++) {
-      if (back && blk == 0)
-        break;
-      const uint64_t b = blk - back;
-      const uint64_t r = gen_raw64 (g.plant_seed, b);
-      const uint64_t kw = (r >> 20) % g.dict_nb, at = (r & 0xFFFFFu) % g.plant_period;
-      const uint64_t lo = g.dict_offsets[kw], len = g.dict_offsets[kw + 1] - lo;
-      const uint64_t rel = off + (uint64_t)back * g.plant_period;
-      if (rel >= at && rel < at + len)
-        return g.dict_symbols[lo + (rel - at)];
-    }
-  }
-  const uint8_t b = (uint8_t)(gen_raw64 (g.seed, i >> 3) >> (8 * (i & 7)));
-  return g.kind == 1 ? (uint8_t)(0x20 + ((b * 95) >> 8)) : b;
-}
-
-__global__ void
-generate_text_kernel (const __grid_constant__ GenParams g) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v * 16 < g.nb; v += stride) {
-    const uint64_t at = v * 16;
-    if (at + 16 <= g.nb) {
-      uint32_t w[4] = { 0, 0, 0, 0 };
-#pragma unroll
-      for (int i = 0; i < 16; i++)
-        w[i >> 2] |= (uint32_t)gen_byte (g, g.first + at + i) << (8 * (i & 3));
-      *reinterpret_cast<uint4 *> (g.dst + at) = make_uint4 (w[0], w[1], w[2], w[3]);
-    } else
-      for (uint64_t i = at; i < g.nb; i++)
-        g.dst[i] = gen_byte (g, g.first + i);
-  }
-}
-
 } // namespace acm

@@ -62,8 +62,7 @@ typedef struct {
   uint64_t capacity;
   const ACState **cursor;  /* optional, in/out: scan continues from *cursor (as acm_match would, aho_corasick.c:447) and *cursor is
                               advanced to the state after the last symbol; 0 = start from state 0, nothing returned */
-  void *stream;            /* cudaStream_t to run on (0 = the library's own stream) */
-  int sorted;              /* 1 (default when 0 is passed via acm_b200_scan): reference order; <0: any order (set semantics) */
+  void *stream;            /* cudaStream_t to run on (0 = a stream of the library's own) */
 } ACMB200Scan;
 
 typedef struct {
@@ -85,6 +84,9 @@ typedef struct {
   uint64_t hot_spans;       /* 32 KiB spans the stride-2 kernel handed to the exact follow-up kernel because a stage overflowed (since creation) */
   uint64_t dfa_event_scans; /* DFA engines: scans whose second pass expanded the events recorded by the first instead of walking the text again */
   uint64_t filter_stride;   /* last scan, filter engine: text positions per filter test (2 = the stride-2 kernel, 1 = every position; 0 = DFA) */
+  uint64_t dense_scans;     /* filter engine: scans that went through the dense mode (text dense in candidates; since creation) */
+  uint64_t patch_count;     /* finalises that patched the resident tables in place instead of rebuilding them (append-only insertions) */
+  uint64_t blob_loads;      /* finalises that uploaded the tables of a blob (acm_b200_load) as they were */
 } ACMB200Stats;
 
 /* Number of CUDA devices visible (0 if none / no driver). */
@@ -107,9 +109,21 @@ int acm_b200_scan (ACMachine *machine, const ACState **cursor, const void *text,
  * Machines created with ACM_CMP_DEFAULT over 1/2/4-byte letters and no letter destructor only.  ids[k] (optional) = keyword id. */
 int acm_b200_insert_keywords (ACMachine *machine, const void *symbols, const uint64_t *offsets, uint64_t nb_keywords, uint32_t *ids);
 
-/* keyword id -> what acm_get_match would have put in the holder (letters, length, value).  The holder follows the
- * reference's rules (acm_matcher_init before, acm_matcher_release after). */
+/* keyword id -> what acm_get_match would have put in the holder (letters, length, value; reference aho_corasick.c:468-481).  The
+ * holder follows the reference's rules (acm_matcher_init before, acm_matcher_release after). */
 int acm_b200_keyword (const ACMachine *machine, uint32_t keyword, MatchHolder *holder);
+
+/* The keyword ids in the order acm_foreach_keyword enumerates the keywords (reference aho_corasick.c:490-531): ids[k] = id of the
+ * k-th keyword its callback receives.  capacity 0 only counts (*nb). */
+int acm_b200_keyword_order (const ACMachine *machine, uint32_t *ids, uint64_t capacity, uint64_t *nb);
+
+/* A finalised dictionary on disk (the reference has no serialisation, aho_corasick.h:45-98).  acm_b200_save writes the packed
+ * dictionary and the table images of the machine's current dictionary (no GPU needed); acm_b200_load returns a machine -- created as
+ * by acm_create (ACM_CMP_DEFAULT, &letter_size, 0) -- whose first batch scan uploads those images without inserting or building
+ * anything; the keyword trie behind the per-symbol API is rebuilt from the packed dictionary the first time it is needed.  Keyword
+ * ids are preserved; user values are not stored.  ACM_CMP_DEFAULT machines over 1/2/4-byte letters only. */
+int acm_b200_save (ACMachine *machine, const char *path);
+ACMachine *acm_b200_load (const char *path, int *error);
 
 /* Bytes per symbol the batch scan expects: the letter size for ACM_CMP_DEFAULT machines with 1/2/4-byte letters, else 4
  * (class ids produced by acm_b200_remap_text). */
@@ -130,12 +144,6 @@ int acm_b200_set_option (ACMachine *machine, const char *key, const char *value)
 int acm_b200_get_stats (ACMachine *machine, ACMB200Stats *stats);
 const char *acm_b200_last_error (void);
 const char *acm_b200_version (void);
-
-/* Bench/test support (not part of the drop-in surface): position-addressable synthetic text, see DESIGN.md "Text generator".
- * kind 0: bytes uniform 0..255; kind 1: printable ASCII 0x20 + (b*95>>8); both with keywords planted every `plant_period`
- * symbols (0 = no plants) taken from the packed dictionary (symbols/offsets, nb_keywords).  The device variant writes device memory. */
-int acm_b200_generate_text (void *dst, int dst_on_device, uint64_t first, uint64_t nb, int kind, uint64_t seed, uint64_t plant_seed,
-                            uint64_t plant_period, const uint8_t *dict_symbols, const uint64_t *dict_offsets, uint64_t dict_nb, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,8 @@ def _lib(kind):
     f("scan").restype, f("scan").argtypes = u64, [vp, vp, u64, u64, vp, u64, ctypes.c_int]
     f("scan_mt").restype, f("scan_mt").argtypes = u64, [vp, vp, u64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     f("incremental").restype, f("incremental").argtypes = ctypes.c_int, []
+    if pfx == "refh":
+        L.refh_foreach_ranks.restype, L.refh_foreach_ranks.argtypes = ctypes.c_size_t, [vp, vp, ctypes.c_size_t]
     if pfx == "acport":
         L.acport_scan_lead.restype = u64
         L.acport_scan_lead.argtypes = [vp, vp, u64, u64, u64, vp, u64, ctypes.c_int, ctypes.POINTER(u32)]
@@ -119,6 +121,13 @@ class Oracle:
 
     def reset_cursor(self):
         self._f("reset_cursor")(self._h)
+
+    def foreach_ranks(self):
+        """Keyword ranks in the order the reference's acm_foreach_keyword enumerates them (reference builds only)."""
+        out = np.zeros(self.nb_keywords, dtype=np.uint32)
+        n = int(self._L.refh_foreach_ranks(self._h, out.ctypes.data, len(out)))
+        assert n == len(out)
+        return out
 
     def _text(self, text):
         if isinstance(text, (bytes, bytearray)):

@@ -113,6 +113,26 @@ refh_insert_many (refh *h, const void *symbols, const uint64_t *offsets, size_t 
   }
 }
 
+/* Ranks of the keywords in the order the reference's acm_foreach_keyword (aho_corasick.c:490-531) enumerates them.  Its callback
+ * has no user argument: the collector is thread-local. */
+static _Thread_local uint32_t *foreach_out;
+static _Thread_local size_t foreach_cap, foreach_nb;
+static void
+foreach_collect (MatchHolder holder) {
+  if (foreach_nb < foreach_cap)
+    foreach_out[foreach_nb] = (uint32_t)((uintptr_t)holder.value - 1);
+  foreach_nb++;
+}
+
+size_t
+refh_foreach_ranks (refh *h, uint32_t *out, size_t cap) {
+  foreach_out = out;
+  foreach_cap = cap;
+  foreach_nb = 0;
+  acm_foreach_keyword (h->machine, foreach_collect);
+  return foreach_nb;
+}
+
 size_t
 refh_nb_keywords (const refh *h) {
   return acm_nb_keywords (h->machine);

@@ -8,8 +8,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+SUPPORT = os.path.join(ROOT, "tests", "support")
+if SUPPORT not in sys.path:
+    sys.path.insert(0, SUPPORT)
 import __graft_entry__ as entry  # noqa: E402
+import textgen  # noqa: E402  (tests/support: the synthetic-text generator, not part of the product library)
 from oracle import pyoracle  # noqa: E402
+
+generate_text = textgen.generate_text
 
 
 def ac75():

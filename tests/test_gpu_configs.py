@@ -7,7 +7,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from helpers import ac75, random_patterns
+from helpers import ac75, generate_text, random_patterns
 from oracle import pyoracle
 
 pytestmark = pytest.mark.gpu
@@ -57,7 +57,7 @@ def test_config5_token_ngrams_incremental_meyer():
 def test_config4_shape_large_dictionary():
     """configs[3] shape at test scale: a dictionary whose tables exceed shared memory by far (300k patterns, ~5M states)."""
     flat, offsets = random_patterns(300_000, seed=4)
-    text = ac75().generate_text(16 << 20, kind=0, plant_period=2048, dict_flat=flat, dict_offsets=offsets)
+    text = generate_text(16 << 20, kind=0, plant_period=2048, dict_flat=flat, dict_offsets=offsets)
     o = pyoracle.Oracle("port", 1)
     o.insert_many(flat=flat, offsets=offsets)
     want = o.scan(text, cap=1 << 22)
@@ -80,7 +80,7 @@ def test_config3_full_size_properties():
     m = ac75().Machine(1)
     ids = m.insert_many(flat=flat, offsets=offsets)
     d_text = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
-    ac75().generate_text(n, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets, device_ptr=d_text.data_ptr())
+    generate_text(n, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets, device_ptr=d_text.data_ptr())
     cap = 1 << 22
     d_out = torch.empty(cap * 16, dtype=torch.uint8, device="cuda")
     total = m.scan_device(d_text.data_ptr(), n, d_matches_ptr=d_out.data_ptr(), capacity=cap)
@@ -151,7 +151,8 @@ def test_dense_fallback_runs_in_segments():
     m.set_option("engine", "filter")
     got = m.scan(text, capacity=1 << 24)
     st = m.stats()
-    assert st["engine"] == "filter" and st["fallback_count"] == 1
+    # a prefix probe finds the text dense in candidates: it goes straight to the dense mode, no doomed sparse attempt
+    assert st["engine"] == "filter" and st["fallback_count"] == 0 and st["dense_scans"] == 1
     assert len(want) > 10_000 and np.array_equal(got, want), (len(got), len(want))
     # with a lead and a base, as a shard would be scanned
     lead = 5_000_000
@@ -159,8 +160,8 @@ def test_dense_fallback_runs_in_segments():
     w2 = want[want["end"] >= lead].copy()
     w2["end"] += 10**12
     assert np.array_equal(got2, w2)
-    # the second dense text went straight to the dense mode (no second doomed attempt) ...
-    assert m.stats()["fallback_count"] == 1
+    # the second dense text went straight to the dense mode too ...
+    assert m.stats()["fallback_count"] == 0 and m.stats()["dense_scans"] == 2
     # ... and a sparse text afterwards is still scanned exactly, after which the fast mode is back
     sparse = rng.integers(4, 256, size=1 << 20).astype(np.uint8)
     k = flat[int(offsets[3]):int(offsets[4])]
@@ -169,5 +170,107 @@ def test_dense_fallback_runs_in_segments():
     want3 = o.scan(sparse, cap=1 << 16)
     for _ in range(2):
         assert np.array_equal(m.scan(sparse, capacity=1 << 16), want3) and len(want3) >= 1
-    assert m.stats()["fallback_count"] == 1
+    assert m.stats()["fallback_count"] == 0
+    m.close(), o.close()
+
+
+@pytest.mark.slow
+def test_config2_full_size_against_the_oracle():
+    """configs[1] at its FULL size: the 1k most frequent words of the novel over 1 GiB of synthetic printable ASCII, every one of the
+    ~72 M records compared with the oracle's, in order."""
+    import gzip
+    import os
+    import re
+    from collections import Counter
+
+    from helpers import ROOT
+
+    novel = gzip.open(os.path.join(ROOT, "tests", "golden", "mrs_dalloway.txt.gz"), "rb").read()
+    cnt = Counter(re.findall(rb"[a-z]+", novel.lower()))
+    words = [w for w, _ in sorted(cnt.items(), key=lambda kv: (-kv[1], kv[0]))[:1000]]
+    flat = np.frombuffer(b"".join(words), dtype=np.uint8)
+    offsets = np.concatenate([[0], np.cumsum([len(w) for w in words])]).astype(np.uint64)
+    n = 1 << 30
+    text = generate_text(n, kind=1, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    m = ac75().Machine(1)
+    m.insert_many(flat=flat, offsets=offsets)
+    got = m.scan(text, capacity=n // 8)
+    st = m.stats()
+    assert st["engine"] == "dfa_smem" and len(got) > 60_000_000
+    o = pyoracle.Oracle("port", 1)
+    o.insert_many(flat=flat, offsets=offsets)
+    piece = 128 << 20  # the oracle's carried cursor makes the pieces one scan; compared piece by piece to bound host memory
+    at = 0
+    for p0 in range(0, n, piece):
+        want = o.scan(text[p0:p0 + piece], base=p0, cap=piece // 8)
+        assert np.array_equal(got[at:at + len(want)], want), p0
+        at += len(want)
+    assert at == len(got)
+    m.close(), o.close()
+
+
+@pytest.mark.slow
+def test_config4_full_dictionary_prefix_and_shard_boundaries():
+    """configs[3] at its stated dictionary size: 1,000,000 patterns (DFA far beyond shared memory).  Records compared with the oracle
+    on a 64 MiB prefix of the 16 GiB text and on windows around every boundary of its 8-way split (scanned as shards: lead + base)."""
+    flat, offsets = random_patterns(1_000_000, seed=0xD1C7)
+    o = pyoracle.Oracle("port", 1)
+    ranks = o.insert_many(flat=flat, offsets=offsets)
+    m = ac75().Machine(1)
+    ids = m.insert_many(flat=flat, offsets=offsets)
+    assert np.array_equal(ranks, ids)
+    pre = 64 << 20
+    text = generate_text(pre, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    want = o.scan(text, cap=1 << 22)
+    got = m.scan(text, capacity=1 << 22)
+    st = m.stats()
+    assert st["engine"] == "filter" and st["nb_keywords"] == m.nb_keywords and st["nb_states"] > 15_000_000
+    assert len(want) > 16_000 and np.array_equal(got, want)
+    lmax = m.max_keyword_length
+    total, world, half = 16 << 30, 8, 1 << 20
+    for (a, b, lead) in ac75().plan_shards(total, world, lmax)[1:]:
+        # the shard that starts at a, cut down to its first MiB, exactly as rank g would scan it ...
+        win = generate_text(half + lead, first=a - lead, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+        right = m.scan(win, lead=lead, base=a - lead, capacity=1 << 16)
+        # ... and the last MiB of the shard before it
+        prev = generate_text(half, first=a - half, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+        left = m.scan(prev, base=a - half, capacity=1 << 16)
+        # the oracle over the two MiB as one text: what a single scan reports there, minus what needs context before the window
+        o.reset_cursor()
+        both = o.scan(np.concatenate([prev, win[lead:]]), base=a - half, cap=1 << 16)
+        mine = np.concatenate([left, right])
+        keep = both["end"] - (both["len"].astype(np.uint64) - 1) >= np.uint64(a - half)  # occurrences wholly inside the two MiB
+        assert np.array_equal(mine[mine["end"] - (mine["len"].astype(np.uint64) - 1) >= np.uint64(a - half)], both[keep]) and len(both) > 300
+    m.close(), o.close()
+
+
+@pytest.mark.slow
+def test_config5_full_dictionary_ten_meyer_rounds():
+    """configs[4] at its stated dictionary size: 200,000 n-grams over a 50k vocabulary, then 10 Meyer rounds of +2,000 n-grams, each
+    followed by a scan of the next slice with the cursor carried (reference aho_corasick_generic_test.c:184-228 interleaves the
+    same way).  Every round's records equal the oracle's carried-cursor scan; the tables are updated, not rebuilt, where possible."""
+    vocab, rounds, add = 50_000, 10, 2000
+    per = 1 << 20
+    stream = zipf_tokens(per * (rounds + 1), vocab, 42)
+    rng = np.random.default_rng(43)
+
+    def cut(k):
+        starts, lens = rng.integers(0, len(stream) - 8, size=k), rng.integers(2, 9, size=k)
+        flat = np.concatenate([stream[a:a + l] for a, l in zip(starts, lens)])
+        return flat, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+
+    o = pyoracle.Oracle("port", 4)
+    m = ac75().Machine(4)
+    flat, offsets = cut(200_000)
+    assert np.array_equal(o.insert_many(flat=flat, offsets=offsets), m.insert_many(flat=flat, offsets=offsets))
+    for r in range(rounds + 1):
+        if r:
+            flat, offsets = cut(add)
+            assert np.array_equal(o.insert_many(flat=flat, offsets=offsets), m.insert_many(flat=flat, offsets=offsets))
+        sl = stream[r * per:(r + 1) * per]
+        want = o.scan(sl, base=r * per, cap=1 << 24)
+        got = m.scan(sl, base=r * per, carry=True, capacity=1 << 24)
+        assert len(want) > 100_000 and np.array_equal(got, want), (r, len(got), len(want))
+    st = m.stats()
+    assert st["engine"] == "filter" and st["symbol_width"] == 4 and st["finalise_count"] == rounds + 1 and st["nb_keywords"] == m.nb_keywords > 190_000
     m.close(), o.close()

@@ -3,7 +3,7 @@ reference's emission order, on the BASELINE.json configs at test scale, for ever
 import numpy as np
 import pytest
 
-from helpers import ac75, best_oracle_kind, config1_keywords, config2_keywords, oracle_records, pack, random_patterns
+from helpers import ac75, best_oracle_kind, config1_keywords, config2_keywords, generate_text, oracle_records, pack, random_patterns
 from oracle import pyoracle
 
 pytestmark = pytest.mark.gpu
@@ -47,7 +47,7 @@ def test_config1_novel(novel, golden_config1, full, engine):
 def test_config2_words_over_ascii(novel, engine):
     words = config2_keywords(novel)
     flat, offsets = pack(words)
-    text = ac75().generate_text(4 << 20, kind=1, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    text = generate_text(4 << 20, kind=1, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
     want = oracle_records(words, text=text, kind="port")
     got, st = gpu_scan(words, text=text, engine=engine)
     if engine == "auto":
@@ -58,7 +58,7 @@ def test_config2_words_over_ascii(novel, engine):
 @pytest.mark.parametrize("engine", ["auto", "dfa_global"])
 def test_config3_random_patterns(engine):
     flat, offsets = random_patterns(5000)
-    text = ac75().generate_text(8 << 20, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
+    text = generate_text(8 << 20, kind=0, plant_period=4096, dict_flat=flat, dict_offsets=offsets)
     want = oracle_records(flat=flat, offsets=offsets, text=text, kind="port")
     got, st = gpu_scan(flat=flat, offsets=offsets, text=text, engine=engine)
     if engine == "auto":
@@ -124,7 +124,7 @@ def test_incremental_rounds_random(engine):
 @pytest.mark.parametrize("engine", ["auto", "dfa_global"])
 def test_lead_base_and_shards(engine):
     flat, offsets = random_patterns(2000, lmin=4, lmax=32, seed=99)
-    text = ac75().generate_text(1 << 20, kind=0, plant_period=1024, dict_flat=flat, dict_offsets=offsets)
+    text = generate_text(1 << 20, kind=0, plant_period=1024, dict_flat=flat, dict_offsets=offsets)
     want = oracle_records(flat=flat, offsets=offsets, text=text, kind="port")
     m = ac75().Machine(1)
     m.insert_many(flat=flat, offsets=offsets)
@@ -335,7 +335,7 @@ def test_dfa_second_pass_from_recorded_events(novel):
     slot per 4 symbols) must fall back to the walk by itself."""
     words = config2_keywords(novel, 300)
     flat, offsets = pack(words)
-    text = ac75().generate_text(3 << 20, kind=1, plant_period=512, dict_flat=flat, dict_offsets=offsets)
+    text = generate_text(3 << 20, kind=1, plant_period=512, dict_flat=flat, dict_offsets=offsets)
     want = oracle_records(words, text=text, kind="port")
     for events in (1, 0):
         m = ac75().Machine(1)
