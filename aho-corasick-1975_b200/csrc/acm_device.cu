@@ -138,7 +138,7 @@ struct acm_device_image {
   int sm_count = 0;
   size_t smem_optin = 0;
   acm_tables tab = {}; /* host images; big arrays are freed after upload except dfa_of_state */
-  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_s2_dist, d_kw_dist, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool;
+  DevBuf d_delta, d_out_offsets, d_out_entries, d_bloom, d_bloom2, d_bloom_s2, d_s2_dist, d_kw_dist, d_qgrams, d_qset, d_edges, d_kw_len, d_kw_off, d_kw_pool, d_kw_meta, d_kw_rpool, d_patches;
   bool two_level = false; /* the filter engine uses the second-level filter in global memory */
   bool stride2 = false;   /* the stride-2 tables (bloom_s2, s2_dist, kw_dist) are resident */
   bool has_rpool = false; /* the reversed keyword pool (kw_meta, kw_rpool) is resident */
@@ -154,7 +154,7 @@ struct acm_device_image {
 static void
 free_image (acm_device_image *img) {
   for (DevBuf *b : { &img->d_delta, &img->d_out_offsets, &img->d_out_entries, &img->d_bloom, &img->d_bloom2, &img->d_bloom_s2, &img->d_s2_dist, &img->d_kw_dist, &img->d_qgrams, &img->d_qset,
-                     &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool })
+                     &img->d_edges, &img->d_kw_len, &img->d_kw_off, &img->d_kw_pool, &img->d_kw_meta, &img->d_kw_rpool, &img->d_patches })
     b->release ();
   for (ScanContext *cx : img->contexts) {
     cx->release ();
@@ -188,8 +188,8 @@ struct DeviceGuard {
 };
 
 static int
-upload (DevBuf &dst, const void *src, size_t bytes, cudaStream_t st) {
-  int rc = dst.ensure (bytes ? (bytes + 15) / 16 * 16 : 16);
+upload (DevBuf &dst, const void *src, size_t bytes, cudaStream_t st, size_t reserve = 0) {
+  int rc = dst.ensure (std::max (reserve, bytes ? (bytes + 15) / 16 * 16 : (size_t)16));
   if (rc)
     return rc;
   if (bytes)
@@ -210,8 +210,8 @@ upload_tables (acm_device_image *img, cudaStream_t st, uint64_t *table_bytes) {
         || (t.qset && (rc = upload (img->d_qset, t.qset, (size_t)16 << (32 - t.qset_shift), st)))
         || (t.bloom_s2 && ((rc = upload (img->d_bloom_s2, t.bloom_s2, (size_t)t.bloom_s2_words * 4, st)) || (rc = upload (img->d_s2_dist, t.s2_dist, (size_t)4 << t.s2_dist_log2, st))
                             || (rc = upload (img->d_kw_dist, t.kw_dist, ((size_t)t.nb_keywords + 1) * 2, st))))
-        || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st)) || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st))
-        || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st))
+        || (rc = upload (img->d_kw_len, t.kw_len, ((size_t)t.nb_keywords + 1) * 4, st, t.builder ? t.builder->kw_cap * 4 : 0))
+        || (rc = upload (img->d_kw_off, t.kw_off, ((size_t)t.nb_keywords + 1) * 8, st, t.builder ? t.builder->kw_cap * 8 : 0)) || (rc = upload (img->d_kw_pool, t.kw_pool, t.kw_pool_bytes, st))
         || (t.kw_meta && ((rc = upload (img->d_kw_meta, t.kw_meta, ((size_t)t.nb_keywords + 1) * 8, st)) || (rc = upload (img->d_kw_rpool, t.kw_rpool, t.kw_rpool_words * 4, st)))))
       return rc;
     bytes = (uint64_t)t.bloom_words * 4 + (t.qgram_slots + t.edge_slots) * sizeof (acm_slot) + t.kw_pool_bytes + (uint64_t)t.nb_keywords * 12
@@ -223,16 +223,20 @@ upload_tables (acm_device_image *img, cudaStream_t st, uint64_t *table_bytes) {
     bytes = t.delta_bytes + ((uint64_t)t.nb_dfa_states - t.out_threshold + 1) * 4 + t.nb_out_entries * sizeof (acm_output);
   }
   CUDA_TRY (cudaStreamSynchronize (st));
+  img->two_level = t.bloom2 != nullptr;
+  img->stride2 = t.bloom_s2 != nullptr;
+  img->has_rpool = t.kw_meta != nullptr;
+  img->prefer_dense = false;
+  img->cand_rate = -1;
+  *table_bytes = bytes;
+  if (t.builder) /* kept for in-place updates after append-only insertions: the host images stay */
+    return ACM_B200_OK;
   /* the big host images are not needed any more */
   free (t.delta), t.delta = nullptr;
   free (t.out_offsets), t.out_offsets = nullptr;
   free (t.out_entries), t.out_entries = nullptr;
   free (t.bloom), t.bloom = nullptr;
-  img->two_level = t.bloom2 != nullptr;
-  img->prefer_dense = false;
-  img->cand_rate = -1;
   free (t.bloom2), t.bloom2 = nullptr;
-  img->stride2 = t.bloom_s2 != nullptr;
   free (t.bloom_s2), t.bloom_s2 = nullptr;
   free (t.s2_dist), t.s2_dist = nullptr;
   free (t.kw_dist), t.kw_dist = nullptr;
@@ -241,11 +245,37 @@ upload_tables (acm_device_image *img, cudaStream_t st, uint64_t *table_bytes) {
   free (t.kw_len), t.kw_len = nullptr;
   free (t.kw_off), t.kw_off = nullptr;
   free (t.kw_pool), t.kw_pool = nullptr;
-  img->has_rpool = t.kw_meta != nullptr;
   free (t.kw_meta), t.kw_meta = nullptr;
   free (t.kw_rpool), t.kw_rpool = nullptr;
   free (t.edges), t.edges = nullptr;
-  *table_bytes = bytes;
+  return ACM_B200_OK;
+}
+
+/* Uploads what an in-place update changed: the appended tails of the per-keyword arrays as contiguous copies, the scattered words
+ * and slots as a patch list applied by one small kernel. */
+static int
+apply_patches (acm_device_image *img, const acm_patch_list &pl) {
+  const acm_tables &t = img->tab;
+  cudaStream_t st = cudaStreamPerThread;
+  const size_t w = (size_t)t.width;
+  if ((pl.kw_first + pl.kw_nb + 1) * 8 > img->d_kw_off.bytes || (pl.kw_first + pl.kw_nb + 1) * 4 > img->d_kw_len.bytes || (pl.pool_first_sym + pl.pool_nb_syms) * w > img->d_kw_pool.bytes)
+    return fail (ACM_B200_ERR_NOMEM, "in-place update: device arrays too small%s", "");
+  if (pl.kw_nb) {
+    CUDA_TRY (cudaMemcpyAsync (img->d_kw_len.as<uint32_t> () + pl.kw_first, t.kw_len + pl.kw_first, pl.kw_nb * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY (cudaMemcpyAsync (img->d_kw_off.as<uint64_t> () + pl.kw_first, t.kw_off + pl.kw_first, pl.kw_nb * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY (cudaMemcpyAsync (img->d_kw_pool.as<unsigned char> () + pl.pool_first_sym * w, reinterpret_cast<const unsigned char *> (t.kw_pool) + pl.pool_first_sym * w, pl.pool_nb_syms * w,
+                               cudaMemcpyHostToDevice, st));
+  }
+  if (pl.nb) {
+    int rc = img->d_patches.ensure (pl.nb * sizeof (acm_patch));
+    if (rc)
+      return rc;
+    CUDA_TRY (cudaMemcpyAsync (img->d_patches.ptr, pl.items, pl.nb * sizeof (acm_patch), cudaMemcpyHostToDevice, st));
+    apply_patches_kernel<<<(unsigned)((pl.nb + 255) / 256), 256, 0, st>>> (img->d_patches.as<acm_patch> (), pl.nb, img->d_bloom.as<uint32_t> (), img->d_bloom2.as<uint32_t> (), img->d_qgrams.as<acm_slot> (),
+                                                                          img->d_qset.as<uint32_t> (), img->d_edges.as<acm_slot> ());
+    CUDA_TRY (cudaGetLastError ());
+  }
+  CUDA_TRY (cudaStreamSynchronize (st));
   return ACM_B200_OK;
 }
 
@@ -270,6 +300,27 @@ finalise_locked (ACMachine *m, int device) {
   const auto t0 = std::chrono::steady_clock::now ();
   /* reuse the image (its device buffers) when nobody is scanning with it and it lives on the right device */
   const bool reuse = img && img->device == device && img->refs == 0;
+  /* append-only insertions since these tables were built (Meyer-style updates between two scans): patch them in place */
+  if (reuse && img->tab.builder && !m->force_rebuild && !m->option_no_patch) {
+    acm_patch_list pl;
+    if (acm_patch_filter_tables (m, &img->tab, &pl) == ACM_B200_OK) {
+      int prc = apply_patches (img, pl);
+      free (pl.items);
+      if (prc)
+        return prc;
+      img->generation = m->generation;
+      m->device_generation = m->generation;
+      ACMB200Stats &s = img->stats;
+      s.nb_states = img->tab.nb_states;
+      s.nb_keywords = img->tab.nb_keywords;
+      s.max_keyword_length = img->tab.lmax;
+      s.finalise_count++;
+      s.patch_count++;
+      s.finalise_ms = std::chrono::duration<double, std::milli> (std::chrono::steady_clock::now () - t0).count ();
+      return ACM_B200_OK;
+    }
+    g_error[0] = 0;
+  }
   acm_device_image *fresh = reuse ? img : new acm_device_image ();
   auto abandon = [&] (int rc) {
     if (!reuse)
@@ -332,6 +383,7 @@ finalise_locked (ACMachine *m, int device) {
     m->device = fresh;
   }
   m->device_generation = m->generation;
+  m->force_rebuild = 0;
   ACMB200Stats &s = fresh->stats;
   s.engine = t.engine;
   s.symbol_width = t.width;
@@ -368,21 +420,23 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
   int rc = ACM_B200_OK;
   if (!strcmp (key, "engine")) {
     snprintf (m->engine_override, sizeof m->engine_override, "%s", strcmp (value, "auto") ? value : "");
-    m->generation++; /* forces a rebuild */
+    m->generation++, m->force_rebuild = 1; /* forces a rebuild */
   } else if (!strcmp (key, "bloom_words"))
-    m->option_bloom_words = strtoull (value, 0, 10), m->generation++;
+    m->option_bloom_words = strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "threads"))
     m->option_threads = strtoull (value, 0, 10);
   else if (!strcmp (key, "stream_bytes"))
     m->option_stream_bytes = strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_smem_kb"))
-    m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++;
+    m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "dfa_events")) /* 0: pass 2 of the DFA engines always walks the text again */
     m->option_no_events = !strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_batches")) /* batches of 32 hits the stride-2 kernel confirms at a time: 1, 2 (default) or 3 */
     m->option_s2_batches = strtoull (value, 0, 10);
+  else if (!strcmp (key, "patch")) /* 0: every insertion between two scans rebuilds the tables (the in-place update is the default) */
+    m->option_no_patch = !strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
-    m->option_no_stride2 = !strtoull (value, 0, 10), m->generation++;
+    m->option_no_stride2 = !strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else
     rc = ACM_B200_ERR_INVALID;
   acm_unlock (m);

@@ -170,6 +170,15 @@ acm_free_tables (struct acm_tables *t) {
   free (t->kw_meta);
   free (t->kw_rpool);
   free (t->edges);
+  if (t->builder) {
+    free (t->builder->full);
+    free (t->builder->parent);
+    free (t->builder->depth);
+    free (t->builder->count);
+    free (t->builder->only_kw);
+    free (t->builder->term_kw);
+    free (t->builder);
+  }
   memset (t, 0, sizeof (*t));
 }
 
@@ -497,14 +506,20 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
   int rc = ACM_B200_ERR_NOMEM;
 
   /* keyword pool (forward symbols) for the tail compares */
-  t->kw_len = malloc (((size_t)nk + 1) * sizeof (uint32_t));
-  t->kw_off = malloc (((size_t)nk + 1) * sizeof (uint64_t));
-  t->kw_pool_bytes = (total_syms + 4) * (uint64_t)t->width;
+  /* dictionaries of moderate size keep their build structures and get room to grow: keywords appended later are then added in
+   * place (acm_patch_filter_tables).  The byte-alphabet path with its reversed pool is rebuilt instead (its stride-2 tables are
+   * optimised as a whole). */
+  const int keep = !m->option_no_patch && total_syms <= (8u << 20) && t->width != 1;
+  const uint64_t kw_cap = keep ? (uint64_t)nk + nk / 4 + 8192 : (uint64_t)nk + 1;
+  const uint64_t pool_cap_syms = keep ? total_syms + total_syms / 4 + 65536 : total_syms + 4;
+  t->kw_len = malloc ((size_t)kw_cap * sizeof (uint32_t));
+  t->kw_off = malloc ((size_t)kw_cap * sizeof (uint64_t));
+  t->kw_pool_bytes = pool_cap_syms * (uint64_t)t->width;
   t->kw_pool = calloc (1, t->kw_pool_bytes);
   /* full (uncompressed) reverse trie, host only */
-  const uint64_t full_slots = pow2_at_least (2 * total_syms + 16);
+  const uint64_t full_slots = pow2_at_least (2 * pool_cap_syms + 16);
   acm_slot *full = malloc (full_slots * sizeof (acm_slot));
-  const size_t max_nodes = (size_t)total_syms + 2;
+  const size_t max_nodes = (size_t)pool_cap_syms + 2;
   uint32_t *parent = malloc (max_nodes * sizeof (uint32_t)), *depth = malloc (max_nodes * sizeof (uint32_t));
   uint32_t *count = calloc (max_nodes, sizeof (uint32_t)), *only_kw = malloc (max_nodes * sizeof (uint32_t));
   uint32_t *term_kw = malloc (max_nodes * sizeof (uint32_t));
@@ -703,6 +718,20 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
     }
   }
   rc = ACM_B200_OK;
+  if (keep && (t->builder = calloc (1, sizeof (*t->builder)))) { /* the build structures stay: appended keywords are added in place */
+    struct acm_filter_builder *b = t->builder;
+    b->full = full, b->full_slots = full_slots, b->full_used = nodes - 1;
+    b->parent = parent, b->depth = depth, b->count = count, b->only_kw = only_kw, b->term_kw = term_kw;
+    b->max_nodes = max_nodes;
+    b->nodes = nodes;
+    b->nq = nq;
+    b->pool_syms = pool_at;
+    b->pool_cap_syms = pool_cap_syms;
+    b->kw_cap = kw_cap;
+    b->edges_used = kept;
+    b->keywords_done = nk;
+    full = 0, parent = depth = count = only_kw = term_kw = 0;
+  }
 done:
   free (full);
   free (parent);
@@ -712,6 +741,225 @@ done:
   free (term_kw);
   free (qkeys);
   free (qnodes);
+  return rc;
+}
+
+/* ---- append-only update of the filter tables --------------------------------------------------------- */
+/* The reference's Meyer bookkeeping (aho_corasick.c:210-240, 318-338) says which fail links and output counts a new keyword
+ * touches; the filter engine has neither -- its tables are keyed by the REVERSE trie -- so the set that changes is smaller still:
+ * the nodes on the new keyword's own right-to-left path.  For each of them the stored form is recomputed from the per-node
+ * keyword counts kept by the builder: an edge is stored iff it leaves a node at depth >= q with two or more keywords below it,
+ * and leads to a tail (one keyword below) or to a node; the q-gram table holds the same for the depth-q node.  A node whose
+ * count goes from 1 to 2 additionally gets the edge of the keyword that used to be alone below it. */
+static int
+patch_push (struct acm_patch_list *pl, uint32_t array, uint64_t index, const void *value, size_t bytes) {
+  if (pl->nb == pl->cap) {
+    const uint64_t cap = pl->cap ? pl->cap * 2 : 4096;
+    struct acm_patch *grown = realloc (pl->items, cap * sizeof (*grown));
+    if (!grown)
+      return ACM_B200_ERR_NOMEM;
+    pl->items = grown;
+    pl->cap = cap;
+  }
+  struct acm_patch *p = &pl->items[pl->nb++];
+  memset (p, 0, sizeof (*p));
+  p->array = array;
+  p->index = index;
+  memcpy (p->value, value, bytes);
+  return ACM_B200_OK;
+}
+
+/* sets key -> (node, keyword) in an open-addressing table, recording the slot if it changed */
+static int
+slot_upsert (acm_slot *tab, uint64_t nslots, uint64_t *used, uint64_t key, uint32_t node, uint32_t keyword, uint32_t array, struct acm_patch_list *pl) {
+  uint64_t j = acm_mix64 (key) & (nslots - 1);
+  while (tab[j].node != ACM_TAB_NONE && tab[j].key != key)
+    j = (j + 1) & (nslots - 1);
+  if (tab[j].node == ACM_TAB_NONE)
+    (*used)++;
+  else if (tab[j].node == node && tab[j].keyword == keyword)
+    return ACM_B200_OK;
+  tab[j] = (acm_slot){ key, node, keyword };
+  return patch_push (pl, array, j, &tab[j], sizeof (acm_slot));
+}
+
+static uint32_t
+pool_symbol (const struct acm_tables *t, uint64_t at) {
+  return t->width == 1 ? ((const uint8_t *)t->kw_pool)[at] : (t->width == 2 ? ((const uint16_t *)t->kw_pool)[at] : ((const uint32_t *)t->kw_pool)[at]);
+}
+
+int
+acm_patch_filter_tables (struct _ac_machine *m, struct acm_tables *t, struct acm_patch_list *pl) {
+  struct acm_filter_builder *b = t->builder;
+  const uint32_t nk = (uint32_t)m->nb_sequences, q = t->q;
+  memset (pl, 0, sizeof (*pl));
+  if (!b || t->engine != ACM_B200_ENGINE_FILTER || t->bloom_s2 || t->kw_meta || nk < b->keywords_done || m->engine_override[0])
+    return ACM_B200_ERR_INVALID;
+  if (m->symbol_kind != ACM_SYM_RAW1 && m->symbol_kind != ACM_SYM_RAW2 && m->symbol_kind != ACM_SYM_RAW4)
+    return ACM_B200_ERR_INVALID; /* class-id alphabets: new letters may add classes */
+  const int shift = t->width == 1 ? 8 : (t->width == 2 ? 16 : 32);
+  /* everything must fit the room the build left */
+  uint64_t new_syms = 0;
+  for (uint32_t r = b->keywords_done; r < nk; r++) {
+    if (m->keywords[r]->depth < q)
+      return ACM_B200_ERR_INVALID; /* a shorter filter window: every table changes */
+    new_syms += m->keywords[r]->depth;
+  }
+  if (nk + 1 > b->kw_cap || b->pool_syms + new_syms + 4 > b->pool_cap_syms || b->nodes + new_syms + 2 > b->max_nodes || (b->full_used + new_syms) * 10 > b->full_slots * 7
+      || (b->edges_used + 3ull * (nk - b->keywords_done)) * 10 > t->edge_slots * 7 || (b->nq + (nk - b->keywords_done)) * 10 > t->qgram_slots * 7
+      || (t->qset && (b->nq + (nk - b->keywords_done)) * 2 > ((uint64_t)4 << (32 - t->qset_shift))))
+    return ACM_B200_ERR_INVALID;
+  pl->kw_first = b->keywords_done;
+  pl->pool_first_sym = b->pool_syms;
+  uint32_t *path = malloc (((size_t)m->lmax + 2) * sizeof (uint32_t)), *path_sym = malloc (((size_t)m->lmax + 2) * sizeof (uint32_t));
+  uint32_t *old_count = malloc (((size_t)m->lmax + 2) * sizeof (uint32_t)), *old_only = malloc (((size_t)m->lmax + 2) * sizeof (uint32_t));
+  int rc = ACM_B200_ERR_NOMEM;
+  if (!path || !path_sym || !old_count || !old_only)
+    goto done;
+  for (uint32_t r = b->keywords_done; r < nk; r++) {
+    const uint32_t len = m->keywords[r]->depth;
+    t->kw_len[r] = len;
+    t->kw_off[r] = b->pool_syms;
+    /* 1. the keyword's right-to-left path in the uncompressed trie (new nodes appended) and its symbols into the pool */
+    uint32_t node = 0, d = 0;
+    uint64_t qkey = 0;
+    int q_created = 0;
+    path[0] = 0;
+    for (const struct _ac_state *s = m->keywords[r]; s->parent; s = s->parent) {
+      const uint32_t sym = acm_symbol_of_state (m, s);
+      const uint64_t at = b->pool_syms + (len - 1 - d);
+      if (t->width == 1)
+        ((uint8_t *)t->kw_pool)[at] = (uint8_t)sym;
+      else if (t->width == 2)
+        ((uint16_t *)t->kw_pool)[at] = (uint16_t)sym;
+      else
+        ((uint32_t *)t->kw_pool)[at] = sym;
+      const uint64_t ekey = ((uint64_t)node << 32) | sym;
+      acm_slot *e = slot_find (b->full, b->full_slots, ekey);
+      int created = 0;
+      if (!e) {
+        b->parent[b->nodes] = node;
+        b->depth[b->nodes] = d + 1;
+        b->count[b->nodes] = 0;
+        b->term_kw[b->nodes] = ACM_TAB_NONE;
+        slot_insert (b->full, b->full_slots, ekey, b->nodes++, ACM_TAB_NONE);
+        b->full_used++;
+        e = slot_find (b->full, b->full_slots, ekey);
+        created = 1;
+      }
+      node = e->node;
+      d++;
+      path[d] = node;
+      path_sym[d] = sym;
+      if (d <= q) {
+        qkey = shift == 32 ? ((d == 1 ? 0 : qkey << 32) | sym) : ((qkey << shift) | sym);
+        if (d == q)
+          q_created = created;
+      }
+    }
+    b->pool_syms += len;
+    /* 2. counts along the path (the old ones are needed below) */
+    for (uint32_t i = 1; i <= len; i++) {
+      old_count[i] = b->count[path[i]];
+      old_only[i] = b->only_kw[path[i]];
+      b->count[path[i]]++;
+      if (b->count[path[i]] == 1)
+        b->only_kw[path[i]] = r;
+    }
+    b->term_kw[path[len]] = r; /* distinct keywords end at distinct nodes */
+    /* 3. the stored form of every node of the path from depth q on */
+    for (uint32_t i = q; i <= len; i++) {
+      const uint32_t v = path[i];
+      const uint32_t to_node = b->count[v] == 1 ? (ACM_TAIL_FLAG | b->only_kw[v]) : v, to_kw = b->count[v] == 1 ? ACM_TAB_NONE : b->term_kw[v];
+      if (i == q) {
+        uint64_t used = b->nq;
+        if ((rc = slot_upsert (t->qgrams, t->qgram_slots, &used, qkey, to_node, to_kw, ACM_PATCH_QGRAMS, pl)))
+          goto done;
+        if (q_created) { /* a q-gram no keyword ended with so far: filter bits, confirmation set */
+          b->nq++;
+          const uint32_t f = acm_fold_key (qkey);
+          const uint32_t w1 = acm_bloom_word (f, t->bloom_words), before1 = t->bloom[w1];
+          t->bloom[w1] |= acm_bloom_mask (f);
+          if (t->bloom[w1] != before1 && (rc = patch_push (pl, ACM_PATCH_BLOOM, w1, &t->bloom[w1], 4)))
+            goto done;
+          if (t->bloom2) {
+            const uint32_t w2 = acm_bloom2_word (f, t->bloom2_words), before2 = t->bloom2[w2];
+            t->bloom2[w2] |= acm_bloom2_mask (f);
+            if (t->bloom2[w2] != before2 && (rc = patch_push (pl, ACM_PATCH_BLOOM2, w2, &t->bloom2[w2], 4)))
+              goto done;
+          }
+          if (t->qset) {
+            const uint32_t key = (uint32_t)qkey, mask = (1u << (32 - t->qset_shift)) - 1u;
+            if (key == ACM_QSET_EMPTY)
+              t->qset_has_empty_key = 1;
+            else
+              for (uint32_t bk = acm_qset_bucket (key, t->qset_shift), placed = 0; !placed; bk = (bk + 1) & mask)
+                for (int c = 0; c < 4 && !placed; c++)
+                  if (t->qset[4 * (size_t)bk + c] == ACM_QSET_EMPTY) {
+                    t->qset[4 * (size_t)bk + c] = key;
+                    placed = 1;
+                    if ((rc = patch_push (pl, ACM_PATCH_QSET, 4 * (uint64_t)bk + c, &key, 4)))
+                      goto done;
+                  }
+          }
+        }
+      } else if (b->count[path[i - 1]] >= 2) {
+        if ((rc = slot_upsert (t->edges, t->edge_slots, &b->edges_used, ((uint64_t)path[i - 1] << 32) | path_sym[i], to_node, to_kw, ACM_PATCH_EDGES, pl)))
+          goto done;
+      }
+      /* a node that had ONE keyword below it and now has two: that keyword's own edge out of it was not stored so far */
+      if (old_count[i] == 1 && i < len + 1) {
+        const uint32_t old = old_only[i], old_len = t->kw_len[old];
+        if (old_len > i) {
+          const uint32_t sym = pool_symbol (t, t->kw_off[old] + (old_len - 1 - i));
+          const acm_slot *e = slot_find (b->full, b->full_slots, ((uint64_t)v << 32) | sym);
+          const uint32_t c = e->node;
+          const uint32_t c_node = b->count[c] == 1 ? (ACM_TAIL_FLAG | b->only_kw[c]) : c, c_kw = b->count[c] == 1 ? ACM_TAB_NONE : b->term_kw[c];
+          if ((rc = slot_upsert (t->edges, t->edge_slots, &b->edges_used, ((uint64_t)v << 32) | sym, c_node, c_kw, ACM_PATCH_EDGES, pl)))
+            goto done;
+        }
+      }
+    }
+  }
+  /* a word or slot may have changed more than once (two new keywords sharing an edge): the kernel applies the list in parallel,
+   * so every entry carries the FINAL content of its target */
+  for (uint64_t i = 0; i < pl->nb; i++) {
+    struct acm_patch *p = &pl->items[i];
+    switch (p->array) {
+      case ACM_PATCH_BLOOM:
+        p->value[0] = t->bloom[p->index];
+        break;
+      case ACM_PATCH_BLOOM2:
+        p->value[0] = t->bloom2[p->index];
+        break;
+      case ACM_PATCH_QSET:
+        p->value[0] = t->qset[p->index];
+        break;
+      case ACM_PATCH_QGRAMS:
+        memcpy (p->value, &t->qgrams[p->index], sizeof (acm_slot));
+        break;
+      case ACM_PATCH_EDGES:
+        memcpy (p->value, &t->edges[p->index], sizeof (acm_slot));
+        break;
+    }
+  }
+  pl->kw_nb = nk - pl->kw_first;
+  pl->pool_nb_syms = b->pool_syms - pl->pool_first_sym;
+  b->keywords_done = nk;
+  t->nb_keywords = nk;
+  t->nb_states = (uint32_t)m->nb_states;
+  t->lmax = m->lmax;
+  t->nb_rev_nodes = b->nodes;
+  rc = ACM_B200_OK;
+done:
+  free (path);
+  free (path_sym);
+  free (old_count);
+  free (old_only);
+  if (rc) {
+    free (pl->items);
+    memset (pl, 0, sizeof (*pl));
+  }
   return rc;
 }
 

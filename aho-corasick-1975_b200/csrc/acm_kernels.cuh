@@ -1547,4 +1547,32 @@ filter_tile_totals_kernel (const __grid_constant__ FilterParams p) {
   p.tile_matches[tile] = total;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* In-place table update after append-only insertions (acm_patch_filter_tables): one thread per changed word / slot.    */
+/* ------------------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__ (256)
+apply_patches_kernel (const acm_patch *__restrict__ patches, uint64_t nb, uint32_t *bloom, uint32_t *bloom2, acm_slot *qgrams, uint32_t *qset, acm_slot *edges) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb)
+    return;
+  const acm_patch p = patches[i];
+  switch (p.array) {
+    case ACM_PATCH_BLOOM:
+      bloom[p.index] = p.value[0];
+      break;
+    case ACM_PATCH_BLOOM2:
+      bloom2[p.index] = p.value[0];
+      break;
+    case ACM_PATCH_QSET:
+      qset[p.index] = p.value[0];
+      break;
+    case ACM_PATCH_QGRAMS:
+      *reinterpret_cast<uint4 *> (qgrams + p.index) = make_uint4 (p.value[0], p.value[1], p.value[2], p.value[3]);
+      break;
+    case ACM_PATCH_EDGES:
+      *reinterpret_cast<uint4 *> (edges + p.index) = make_uint4 (p.value[0], p.value[1], p.value[2], p.value[3]);
+      break;
+  }
+}
+
 } // namespace acm

@@ -140,6 +140,37 @@ typedef struct {
   uint32_t length;
 } acm_output; /* one entry of the CSR output sets of the DFA engines */
 
+/* Host-only structures of the filter engine that survive a finalise, so that keywords appended later (Meyer-style insertions
+ * between two scans) are added to the resident tables in place instead of rebuilding everything (acm_patch_filter_tables): the
+ * uncompressed reverse trie with its per-node keyword counts.  Kept only for dictionaries of moderate size. */
+struct acm_filter_builder {
+  acm_slot *full;      /* uncompressed reverse trie: (node << 32 | symbol) -> child */
+  uint64_t full_slots, full_used;
+  uint32_t *parent, *depth, *count, *only_kw, *term_kw;
+  size_t max_nodes;
+  uint32_t nodes;
+  uint64_t nq;          /* distinct q-grams (keys of the q-gram table / set / filter) */
+  uint64_t pool_syms;   /* symbols used in kw_pool */
+  uint64_t pool_cap_syms, kw_cap; /* capacities (host arrays are allocated with room to grow) */
+  uint64_t rpool_words_used, rpool_cap_words;
+  uint64_t edges_used, qset_cells;
+  uint32_t keywords_done; /* keywords 0 .. keywords_done-1 are in the tables */
+};
+
+/* One in-place change of a device table, applied by a small kernel after an append-only update (acm_device.cu). */
+enum { ACM_PATCH_BLOOM = 0, ACM_PATCH_BLOOM2 = 1, ACM_PATCH_QGRAMS = 2, ACM_PATCH_QSET = 3, ACM_PATCH_EDGES = 4 };
+struct acm_patch {
+  uint32_t array, pad;
+  uint64_t index;    /* element index: 32-bit words for the filters and the q-gram set cells, 16-byte slots for the hash tables */
+  uint32_t value[4]; /* one word, or a whole slot */
+};
+struct acm_patch_list {
+  struct acm_patch *items;
+  uint64_t nb, cap;
+  /* the appended tails of the per-keyword arrays, uploaded as contiguous copies: [first, first + nb) */
+  uint64_t kw_first, kw_nb, pool_first_sym, pool_nb_syms, rpool_first_word, rpool_nb_words;
+};
+
 struct acm_tables {
   int engine;        /* ACM_B200_ENGINE_* */
   int width;         /* bytes per device symbol: 1, 2 or 4 */
@@ -186,6 +217,7 @@ struct acm_tables {
   uint32_t *kw_meta;          /* width 1: keyword id -> {length, first word in kw_rpool} (one 8-byte load) */
   uint32_t *kw_rpool;         /* width 1: every keyword's bytes REVERSED, each keyword padded to whole 32-bit words */
   uint64_t kw_rpool_words;
+  struct acm_filter_builder *builder; /* host only (never stored in a blob); non-null: the host images above stay allocated */
 };
 
 #ifdef __cplusplus
@@ -194,6 +226,9 @@ extern "C" {
 struct _ac_machine;
 /* Builds the images for the machine's current dictionary; returns 0 or an ACM_B200_ERR_* code. */
 int acm_build_tables (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget, uint64_t smem_optin);
+/* Adds the keywords appended since the tables were built (ids t->builder->keywords_done .. nb_keywords-1) to the host images in
+ * place and lists what changed.  Returns 0, or ACM_B200_ERR_INVALID when the update cannot be done in place (then rebuild). */
+int acm_patch_filter_tables (struct _ac_machine *m, struct acm_tables *t, struct acm_patch_list *patches);
 void acm_free_tables (struct acm_tables *t);
 /* Device symbol of the edge entering host state s (raw value or class id). */
 uint32_t acm_symbol_of_state (const struct _ac_machine *m, const struct _ac_state *s);

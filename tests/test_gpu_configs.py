@@ -273,4 +273,50 @@ def test_config5_full_dictionary_ten_meyer_rounds():
         assert len(want) > 100_000 and np.array_equal(got, want), (r, len(got), len(want))
     st = m.stats()
     assert st["engine"] == "filter" and st["symbol_width"] == 4 and st["finalise_count"] == rounds + 1 and st["nb_keywords"] == m.nb_keywords > 190_000
+    assert st["patch_count"] == rounds  # every Meyer round updated the resident tables in place
     m.close(), o.close()
+
+
+@pytest.mark.parametrize("width,alphabet", [(4, 50_000), (4, 40), (2, 300), (2, 6)])
+def test_in_place_table_update_equals_rebuild(width, alphabet):
+    """Append-only insertions between scans (Meyer-style): the tables patched in place give the records of the oracle's
+    carried-cursor scan and of a machine that rebuilds everything (option patch=0), for nested / suffix / extending keywords too."""
+    rng = np.random.default_rng(width * 1000 + alphabet)
+    dt = {2: np.uint16, 4: np.uint32}[width]
+    n = 400_000
+    text = rng.integers(0, alphabet, size=n).astype(dt)
+
+    def cut(k, lmin=2):
+        out = []
+        for _ in range(k):
+            a, l = int(rng.integers(0, n - 12)), int(rng.integers(lmin, 10))
+            kw = text[a:a + l].copy()
+            r = rng.random()
+            if r < 0.2 and out:  # an earlier keyword with symbols prepended: the old one becomes a proper suffix
+                kw = np.concatenate([text[a:a + 2], out[int(rng.integers(0, len(out)))]])
+            elif r < 0.3 and out and len(out[-1]) > 3:  # a proper suffix of an earlier keyword
+                kw = out[-1][1:].copy()
+            out.append(kw)
+        return out
+
+    o = pyoracle.Oracle("port", width)
+    m, full = ac75().Machine(width), ac75().Machine(width)
+    full.set_option("patch", 0)
+    first = cut(3000)
+    for mach in (o, m, full):
+        mach.insert_many(first)
+    rounds, per = 8, n // 9
+    for r in range(rounds + 1):
+        if r:
+            more = cut(int(rng.integers(1, 400)))
+            ids = [mach.insert_many(more) for mach in (o, m, full)]
+            assert np.array_equal(ids[0], ids[1]) and np.array_equal(ids[0], ids[2])
+        sl = text[r * per:(r + 1) * per]
+        want = o.scan(sl, base=r * per, cap=1 << 22)
+        got = m.scan(sl, base=r * per, carry=True, capacity=1 << 22)
+        ref = full.scan(sl, base=r * per, carry=True, capacity=1 << 22)
+        assert np.array_equal(got, want) and np.array_equal(ref, want), (r, len(got), len(ref), len(want))
+    # (a round may still rebuild: when the room the build left for growth is used up)
+    assert m.stats()["patch_count"] >= rounds - 2 and full.stats()["patch_count"] == 0 and full.stats()["finalise_count"] == rounds + 1
+    for mach in (o, m, full):
+        mach.close()
