@@ -433,6 +433,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_no_events = !strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_batches")) /* batches of 32 hits the stride-2 kernel confirms at a time: 1, 2 (default) or 3 */
     m->option_s2_batches = strtoull (value, 0, 10);
+  else if (!strcmp (key, "dfa_tma")) /* 0: the DFA count pass loads its chunks per thread instead of staging them through shared memory with TMA */
+    m->option_no_tma = !strtoull (value, 0, 10);
   else if (!strcmp (key, "patch")) /* 0: every insertion between two scans rebuilds the tables (the in-place update is the default) */
     m->option_no_patch = !strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
@@ -454,6 +456,31 @@ acm_b200_get_stats (ACMachine *m, ACMB200Stats *stats) {
     memset (stats, 0, sizeof (*stats));
   acm_unlock (m);
   return ACM_B200_OK;
+}
+
+/* ---- TMA descriptor of the DFA count pass --------------------------------------------------------------------------------- */
+/* The text as a 2-D byte tensor: `rows` rows of `chunk` bytes (row = chunk of the DFA walk), fetched in boxes of 32 rows x 32 bytes.
+ * cuTensorMapEncodeTiled is a driver entry point: it is looked up at run time, so libac75.so does not link libcuda. */
+static int
+encode_chunk_tensor (CUtensorMap *map, const void *text, uint64_t chunk, uint64_t rows) {
+  typedef CUresult (*encode_fn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError ();
+      return ACM_B200_ERR_CUDA;
+    }
+    encode = reinterpret_cast<encode_fn> (fn);
+  }
+  const cuuint64_t dims[2] = { chunk, rows }, strides[1] = { chunk };
+  const cuuint32_t box[2] = { kTmaStageBytes, 32 }, elem[2] = { 1, 1 };
+  return encode (map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *> (text), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? ACM_B200_OK
+             : ACM_B200_ERR_CUDA;
 }
 
 /* ---- device scan of counts ------------------------------------------------------------------------------------------ */
@@ -516,7 +543,19 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uin
   p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 1ull << 30)); /* the kernels keep chunk-relative positions in 32 bits */
   if (kShared && sizeof (Entry) == 2 && !m->option_threads)
     p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 32768)); /* positions inside a chunk fit 16 bits (pass 1 events); huge texts: several chunks per thread */
+  /* pass 1 with the text staged through shared memory by the TMA unit (dfa_scan_tma_kernel): shared-memory engine whose tables leave
+   * room for the stage buffers; chunks of whole 32-byte stages; the chunks that lie wholly inside the text are the rows of the tensor,
+   * a last partial chunk goes through the walking kernel */
+  const size_t tma_smem = kTmaCtaBytes + count_smem + 16; /* (+ the zero entry that ends the records-per-state table) */
+  bool use_tma = kShared && sizeof (Entry) == 2 && p.counts_in_smem && tma_smem <= img->smem_optin && job.n < (1ull << 32) && !m->option_no_tma && !m->option_threads && p.warm < 4096;
+  if (use_tma) {
+    /* small chunks: the partial last chunk, which one thread of the walking kernel does after this pass, stays short */
+    p.chunk = std::min<uint64_t> (p.chunk, std::max<uint64_t> (min_chunk, 2048));
+    p.chunk = (p.chunk + 31) / 32 * 32;
+    use_tma = job.n / p.chunk >= 1 && p.chunk >= (p.warm + 31) / 32 * 32 && ((uintptr_t)job.d_text & 15) == 0;
+  }
   p.nchunks = (job.n + p.chunk - 1) / p.chunk;
+  p.tma_chunks = use_tma ? job.n / p.chunk : 0;
   const unsigned grid = (unsigned)std::min<uint64_t> ((p.nchunks + threads - 1) / threads, (uint64_t)img->sm_count * blocks_per_sm);
 
   int rc;
@@ -552,9 +591,29 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uin
   CUDA_TRY (cudaFuncSetAttribute (emit_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
   cx->stats.smem_bytes = emit_smem;
 
+  CUtensorMap tmap;
+  if (use_tma && encode_chunk_tensor (&tmap, job.d_text, p.chunk, p.tma_chunks) != ACM_B200_OK) {
+    use_tma = false; /* no TMA descriptor: the walking kernel does everything */
+    p.tma_chunks = 0;
+    g_error[0] = 0;
+  }
   CUDA_TRY (cudaEventRecord (cx->ev[0], job.st));
-  count_k<<<grid, threads, count_smem, job.st>>> (p);
-  CUDA_TRY (cudaGetLastError ());
+  if (use_tma) {
+    void (*tma_k) (const DfaParams, const CUtensorMap) = use_events ? dfa_scan_tma_kernel<true> : dfa_scan_tma_kernel<false>;
+    CUDA_TRY (cudaFuncSetAttribute (tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+    const unsigned tgrid = (unsigned)std::min<uint64_t> ((p.tma_chunks + 1023) / 1024, (uint64_t)img->sm_count);
+    tma_k<<<tgrid, 1024, tma_smem, job.st>>> (p, tmap);
+    CUDA_TRY (cudaGetLastError ());
+    cx->stats.total_kernel_launches += 1;
+    cx->stats.dfa_tma_scans++;
+  }
+  if (p.tma_chunks < p.nchunks) { /* everything, or the partial last chunk */
+    p.first_chunk = p.tma_chunks;
+    const unsigned rgrid = (unsigned)std::min<uint64_t> ((p.nchunks - p.tma_chunks + threads - 1) / threads, (uint64_t)grid);
+    count_k<<<rgrid, threads, count_smem, job.st>>> (p);
+    CUDA_TRY (cudaGetLastError ());
+    p.first_chunk = 0;
+  }
   CUDA_TRY (cudaEventRecord (cx->ev[1], job.st));
   if ((rc = device_exclusive_scan (cx, p.chunk_counts, p.nchunks, cx->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
     return rc;
@@ -908,6 +967,7 @@ merge_stats (ACMB200Stats &into, const ACMB200Stats &scan) {
   into.hot_spans += scan.hot_spans;
   into.dfa_event_scans += scan.dfa_event_scans;
   into.dense_scans += scan.dense_scans;
+  into.dfa_tma_scans += scan.dfa_tma_scans;
 }
 
 static int

@@ -380,7 +380,7 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
   /* The stage capacity depends on the hit rate, which depends on the filter size, which is what the stages leave of the shared
    * memory the kernel may use (smem_optin here): start from a small stage and grow it until the expected hits fit with a margin. */
   uint32_t hit_cap = 64;
-  for (int attempt = 0; attempt < 10; attempt++, hit_cap += 32) {
+  for (int attempt = 0; attempt < 22; attempt++, hit_cap += 32) {
     const uint64_t room = smem_optin - 2048;
     if (room < 32ull * ACM_S2_WARP_BYTES (hit_cap) + 4096)
       break;
@@ -399,7 +399,7 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
       if (!b.cnt || !b.pop)
         goto done;
       memset (dist, 0xFF, (size_t)nk * 2);
-      for (int pass = 0; pass < 4; pass++)
+      for (int pass = 0; pass < (nk > 300000 ? 2 : 4); pass++) /* (huge dictionaries: two rounds of re-choosing are enough) */
         for (uint32_t i = 0; i < nk; i++) {
           const uint32_t r = order[i], len = t->kw_len[r];
           if (parent[r] != ACM_NONE)
@@ -431,8 +431,14 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
       fp2 += f * f;
     }
     const double hit_rate = fp2 / b.words + 2.0 * (double)roots / 16777216.0;
-    if (hit_rate * 1024 * 1.5 + 32 > hit_cap)
-      continue; /* expected hits per tile (1024 tests) must leave a 1.5x margin in the stage */
+    if (hit_rate * 1024 * 1.5 + 32 > hit_cap) { /* expected hits per tile (1024 tests) must leave a 1.5x margin in the stage */
+      /* jump to the stage this hit rate asks for (+ one step: the smaller filter will let a little more through) instead of
+       * growing by 32 and redoing the window choice each time -- with 10^6 keywords one choice takes seconds */
+      const uint32_t want_cap = ((uint32_t)(hit_rate * 1024 * 1.5 + 32) + 31) / 32 * 32 + 32;
+      if (want_cap > hit_cap + 32)
+        hit_cap = want_cap - 32; /* the loop adds 32 */
+      continue;
+    }
     for (uint32_t i = 0; i < nk; i++) { /* ascending length: the suffix keyword's distances are final */
       const uint32_t r = order[i];
       if (parent[r] != ACM_NONE) {
@@ -710,7 +716,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
   }
   /* stride-2 filter (acm_tables.h): byte alphabet, every keyword at least 4 bytes long, dictionary small enough for the
    * shared-memory level to stay selective with two keys per keyword */
-  if (t->width == 1 && q == 4 && nk && !t->bloom2 && smem_optin >= 65536) {
+  if (t->width == 1 && q == 4 && nk && smem_optin >= 65536) {
     const int s2rc = build_stride2 (m, t, smem_optin);
     if (s2rc != ACM_B200_OK) {
       rc = s2rc;

@@ -22,6 +22,7 @@
 #pragma once
 #include "acm_tables.h"
 #include "acm_b200.h"
+#include <cuda.h> /* CUtensorMap: the TMA descriptor of the DFA count pass */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -139,6 +140,8 @@ struct DfaParams {
   const acm_output *out_entries;
   uint32_t nb_out_states;        /* states >= out_threshold */
   uint32_t counts_in_smem;       /* pass 1 keeps a uint16 records-per-state table in shared memory (small dictionaries) */
+  uint64_t first_chunk;          /* the walking kernels start at this chunk (the chunks before it were done by the TMA-staged pass) */
+  uint64_t tma_chunks;           /* chunks [0, tma_chunks) lie wholly inside the text: rows of the TMA tensor */
   uint32_t *chunk_counts;        /* pass 1 out */
   const uint64_t *chunk_offsets; /* pass 2 in */
   ACMB200Match *matches;
@@ -178,7 +181,7 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
   const uint32_t K = p.K, thr = p.out_threshold;
   const bool smem_counts = !kEmit && p.counts_in_smem;
 
-  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t c = p.first_chunk + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < p.nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t start = c * p.chunk;
     const uint64_t end = min (p.n, start + p.chunk);
     const uint64_t report_from = max (start, p.lead);
@@ -268,6 +271,158 @@ dfa_scan_kernel (const __grid_constant__ DfaParams p) {
       if (nev > p.events_per_chunk)
         atomicExch (p.events_overflow, 1u);
     }
+  }
+}
+
+/* Pass 1 of the shared-memory DFA engine with the text staged through shared memory by the TMA unit.
+ *
+ * The text is a 2-D tensor of bytes: row = chunk, `chunk` bytes per row (acm_device.cu encodes the tensor map per scan).  A warp owns
+ * 32 neighbouring chunks; one cp.async.bulk.tensor.2d per stage brings the next 32 bytes of ALL 32 chunks (a 32 x 32-byte box: one
+ * sector per row, 1 KB) into the warp's stage buffer and completes on the warp's mbarrier, two stages in flight.  Every lane then
+ * takes its row with two 16-byte shared loads.  What the per-thread loads of dfa_scan_kernel cost -- 32 lines touched per warp-wide
+ * instruction, address arithmetic, a dependent chain of global round trips per lane -- is one instruction of one lane here.
+ * The warm-up (max keyword length - 1 bytes before the chunk) is the tail of the row above: the same box one row up.
+ * The walk itself records events WITHOUT branching (an output state is met every ~15 bytes of config 2's text, so a branch on it
+ * splits the warp at almost every step): predicated store through a clamped running pointer, predicated count. */
+constexpr uint32_t kTmaStageBytes = 32;                 /* per chunk and stage */
+constexpr uint32_t kTmaWarpBytes = 2 * 32 * kTmaStageBytes; /* two stages of 32 rows */
+constexpr uint32_t kTmaCtaBytes = 32 * kTmaWarpBytes + 32 * 2 * 8; /* stage buffers of 32 warps + their mbarriers */
+
+__device__ __forceinline__ uint32_t
+smem_u32 (const void *p) {
+  return (uint32_t)__cvta_generic_to_shared (p);
+}
+
+template <bool kEvents>
+__global__ void __launch_bounds__ (1024, 1)
+dfa_scan_tma_kernel (const __grid_constant__ DfaParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__ (128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *stage_buf = smem + (size_t)warp * kTmaWarpBytes;
+  uint64_t *mbar = reinterpret_cast<uint64_t *> (smem + 32 * kTmaWarpBytes) + 2 * warp;
+  uint8_t *s_class = smem + kTmaCtaBytes;
+  uint16_t *s_delta = reinterpret_cast<uint16_t *> (smem + kTmaCtaBytes + 256);
+  const size_t delta_bytes = ((size_t)p.nb_states * p.K * 2 + 15) / 16 * 16;
+  uint16_t *s_counts = reinterpret_cast<uint16_t *> (smem + kTmaCtaBytes + 256 + delta_bytes);
+  if (lane == 0) {
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32 (&mbar[0])));
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32 (&mbar[1])));
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_class[i] = p.class_of_byte[i];
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *> (p.delta);
+    uint4 *dst = reinterpret_cast<uint4 *> (s_delta);
+    for (uint32_t i = threadIdx.x; i < delta_bytes / 16; i += blockDim.x)
+      dst[i] = src[i];
+  }
+  for (uint32_t i = threadIdx.x; i <= p.nb_out_states; i += blockDim.x)
+    s_counts[i] = i < p.nb_out_states ? (uint16_t)(p.out_offsets[i + 1] - p.out_offsets[i]) : (uint16_t)0;
+  __syncthreads ();
+
+  const uint32_t K = p.K, thr = p.out_threshold;
+  const uint32_t chunk = (uint32_t)p.chunk, warm_pad = (p.warm + kTmaStageBytes - 1) / kTmaStageBytes * kTmaStageBytes;
+  const uint32_t warm_stages = warm_pad / kTmaStageBytes, stages = warm_stages + chunk / kTmaStageBytes;
+  uint32_t g = 0; /* stages issued so far by this warp: buffer g & 1, mbarrier phase (g >> 1) & 1 */
+  /* lane 0 asks the TMA unit for stage k of the warp's rows [row0, row0 + 32): the warm-up stages read the row above */
+  auto issue = [&] (uint32_t k, uint64_t row0, uint32_t slot) {
+    if (lane == 0) {
+      const int32_t x = k < warm_stages ? (int32_t)(chunk - warm_pad + k * kTmaStageBytes) : (int32_t)((k - warm_stages) * kTmaStageBytes);
+      const int32_t y = (int32_t)row0 - (k < warm_stages ? 1 : 0);
+      const uint32_t bar = smem_u32 (&mbar[slot]), dst = smem_u32 (stage_buf + slot * 32 * kTmaStageBytes);
+      asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32u * kTmaStageBytes) : "memory");
+      asm volatile ("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(&tmap), "r"(bar), "r"(x), "r"(y)
+                    : "memory");
+    }
+  };
+
+  for (uint64_t row0 = ((uint64_t)blockIdx.x * 32 + warp) * 32; row0 < p.tma_chunks; row0 += (uint64_t)gridDim.x * 32 * 32) {
+    const uint64_t c = row0 + lane;
+    const bool have = c < p.tma_chunks; /* rows beyond the tensor read as zeros and are not reported */
+    const uint64_t start = c * p.chunk;
+    /* chunk 0 starts from the carried cursor's state and has no warm-up; the others re-read the tail of the row above from state 0 */
+    uint32_t state = c == 0 ? p.init_state : 0;
+    const int32_t report_rel = have ? (int32_t)min (p.lead > start ? p.lead - start : (uint64_t)0, p.chunk) : (int32_t)chunk;
+    uint32_t count = 0;
+    uint32_t *const ev_first = kEvents ? p.events + c * p.events_per_chunk : nullptr;
+    const uint32_t ev_cap_m1 = kEvents ? p.events_per_chunk - 1 : 0; /* a chunk with more events keeps overwriting its last slot */
+    const uint32_t nb_out = p.nb_out_states; /* s_counts[nb_out] == 0 */
+    const uint32_t ev_slot0 = (uint32_t)(c * p.events_per_chunk); /* (the host uses this kernel only while the event buffer has fewer than 2^32 slots) */
+    uint32_t nev = 0, ev_slot = ev_slot0;
+
+    issue (0, row0, g & 1);
+    if (stages > 1)
+      issue (1, row0, (g + 1) & 1);
+    for (uint32_t k = 0; k < stages; k++, g++) {
+      const uint32_t slot = g & 1, phase = (g >> 1) & 1;
+      { /* wait for the stage */
+        const uint32_t bar = smem_u32 (&mbar[slot]);
+        uint32_t done = 0;
+        while (!done)
+          asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+      }
+      const uint4 *row = reinterpret_cast<const uint4 *> (stage_buf + slot * 32 * kTmaStageBytes + lane * kTmaStageBytes);
+      const uint4 va = row[0], vb = row[1];
+      /* the shared-memory pipe is this kernel's bottleneck, so the two loads above can sit in its queue for a long time; the TMA unit
+       * writes through the async proxy and does not know about them: a proxy fence orders this lane's reads before the refill that
+       * lane 0 asks for after the warp barrier (without it about one stage in 10,000 was overwritten before it had been read) */
+      asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp (); /* every lane has its 32 bytes: the buffer may be refilled */
+      if (k + 2 < stages)
+        issue (k + 2, row0, slot);
+      const uint32_t w[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
+      if (k < warm_stages) { /* warm-up: walked, never reported */
+        if (c != 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            state = s_delta[state * K + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
+        }
+      } else {
+        const int32_t rel0 = (int32_t)((k - warm_stages) * kTmaStageBytes);
+        if (rel0 >= report_rel && (!kEvents || nev + 32 <= p.events_per_chunk)) {
+          /* usual stage: every byte reportable, room for 32 more events.  Straight-line: the records of the state come from a
+           * table that has a zero entry for "no output" (index clamped, no predicate), the event goes out through ONE predicated
+           * store at a running 32-bit slot index */
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            state = s_delta[state * K + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
+            const uint32_t o = state - thr; /* wraps for states without outputs */
+            count += s_counts[min (o, nb_out)];
+            if (kEvents) {
+              if (state >= thr)
+                p.events[ev_slot] = (o << 16) + (uint32_t)rel0 + (uint32_t)i;
+              ev_slot += state >= thr;
+            }
+          }
+          if (kEvents)
+            nev = ev_slot - ev_slot0;
+        } else { /* the stage that holds the caller's lead: per-byte test */
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            state = s_delta[state * K + s_class[(w[i >> 2] >> (8 * (i & 3))) & 0xFFu]];
+            if (state >= thr && rel0 + i >= report_rel) {
+              const uint32_t o = state - thr;
+              count += s_counts[o];
+              if (kEvents) {
+                ev_first[min (nev, ev_cap_m1)] = (uint32_t)(rel0 + i) | (o << 16);
+                nev++;
+                ev_slot = ev_slot0 + min (nev, ev_cap_m1);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (have) {
+      p.chunk_counts[c] = count;
+      if (kEvents) {
+        p.chunk_events[c] = nev;
+        if (nev > p.events_per_chunk)
+          atomicExch (p.events_overflow, 1u);
+      }
+    }
+    __syncwarp ();
   }
 }
 

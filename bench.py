@@ -296,7 +296,12 @@ def measure(name, cfg, args, ac75, torch, dist, rank, world, local, scaling, ste
         for _ in range(max(warmup, 1)):
             local_matches = step_device()
             exchange(local_matches)
-        if warmup == 0 or time.time() - t_load > 0.25:
+        more = 0 if (warmup == 0 or time.time() - t_load > 0.25) else 1
+        if world > 1:  # every rank must leave the loop after the same number of collectives: rank 0's clock decides
+            flag = torch.tensor([more], dtype=torch.int64, device="cuda")
+            dist.broadcast(flag, 0)
+            more = int(flag.item())
+        if not more:
             break
     assert local_matches <= cap, f"record buffer too small: {local_matches} > {cap}"
     st0 = m.stats()

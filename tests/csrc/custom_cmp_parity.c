@@ -1,6 +1,9 @@
 /* GPU parity for machines with a user comparator (reference aho_corasick_generic_test.c:48-54: wchar_t letters, case-insensitive).
  * The batch scan over class ids (acm_b200_remap_text + acm_b200_scan) must report exactly what the per-symbol loop
  * acm_match / acm_get_match reports on the same machine, including insertions between scans on a carried cursor.
+ * Every round also prints the FNV-1a-64 of the GPU records (end, id, len as three little-endian u64, emission order -- the hash of
+ * SURVEY.md Appendix B): the Python side of the test recomputes it from the ORACLE on a case-folded copy of the same workload, so
+ * the GPU result is held against the reference itself, not only against this library's own host loop.
  * Exit status 0 = identical.  Usage: custom_cmp_parity <text file> */
 #include "acm_b200.h"
 #include <stdint.h>
@@ -15,6 +18,20 @@ alphacmp (const void *k, const void *t, const void *arg) {
   (void)arg;
   wint_t a = towlower (*(const wint_t *)k), b = towlower (*(const wint_t *)t);
   return a > b ? 1 : (a < b ? -1 : 0);
+}
+
+static uint64_t
+fnv1a64_records (const ACMB200Match *r, uint64_t n) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint64_t i = 0; i < n; i++) {
+    const uint64_t w[3] = { r[i].end, r[i].keyword, r[i].length };
+    for (int k = 0; k < 3; k++)
+      for (int b = 0; b < 8; b++) {
+        h ^= (w[k] >> (8 * b)) & 0xFFu;
+        h *= 0x100000001b3ull;
+      }
+  }
+  return h;
 }
 
 static size_t
@@ -94,7 +111,7 @@ main (int argc, char **argv) {
       fprintf (stderr, "round %zu: loop %zu records, gpu %llu, cursors %s\n", r, na, (unsigned long long)nb, loop_cursor == gpu_cursor ? "equal" : "DIFFER");
       rc = 1;
     } else
-      printf ("round %zu: %zu keywords, %zu records identical\n", r, acm_nb_keywords (m), na);
+      printf ("round %zu: %zu keywords, %zu records identical, gpu fnv %016llx\n", r, acm_nb_keywords (m), na, (unsigned long long)fnv1a64_records (b, nb));
   }
   ACMB200Stats st;
   acm_b200_get_stats (m, &st);

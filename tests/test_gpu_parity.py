@@ -178,6 +178,34 @@ def test_custom_comparator_machine_through_c_abi(tmp_path, novel):
     r = subprocess.run([str(exe), str(txt)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("records identical") == 4 and "width 4" in r.stdout
+    # the same workload through the ORACLE (case folded by hand: under the comparator "The" and "the" are one keyword and one text):
+    # keyword ids, record counts and the FNV-1a-64 of the records (SURVEY Appendix B's hash) must be what the GPU printed
+    import re
+
+    raw = txt.read_bytes()[: 1 << 20]
+    low = np.frombuffer(raw.lower(), dtype=np.uint8)
+    o = pyoracle.Oracle(best_oracle_kind(), 1)
+    alpha = np.array([chr(c).isascii() and chr(c).isalpha() for c in range(256)])[np.frombuffer(raw, dtype=np.uint8)]
+    rounds, per, nk, n = 4, len(raw) // 4, 0, len(raw)
+    printed = re.findall(r"round (\d): (\d+) keywords, (\d+) records identical, gpu fnv ([0-9a-f]{16})", r.stdout)
+    assert len(printed) == rounds
+    for rnd in range(rounds):
+        i = rnd * per
+        while i < (rnd + 1) * per and nk < 4000:
+            if alpha[i]:
+                j = i
+                while j < n and alpha[j]:
+                    j += 1
+                before = o.nb_keywords
+                o.insert(bytes(low[i:j]))
+                nk += o.nb_keywords > before
+                i = j + 37
+            else:
+                i += 1
+        want = o.scan(low[rnd * per:(rnd + 1) * per], base=rnd * per, cap=2_000_000)
+        assert (int(printed[rnd][1]), int(printed[rnd][2])) == (o.nb_keywords, len(want)), (rnd, printed[rnd], o.nb_keywords, len(want))
+        assert int(printed[rnd][3], 16) == pyoracle.fnv1a64_records(want), rnd
+    o.close()
 
 
 @pytest.mark.parametrize("engine", ["dfa_smem", "dfa_global", "filter"])
