@@ -161,6 +161,7 @@ acm_b200_load (const char *path, int *error) {
     const int na = blob_arrays (t, arr);
     for (int i = 0; i < na; i++)
       *arr[i].ptr = 0; /* the pointers of the saving process mean nothing here */
+    t->builder = 0;    /* (nor its build structures: tables from a blob are rebuilt, not patched, after an insertion) */
     for (int i = 0; i < na; i++) {
       uint64_t bytes;
       if (!get (f, &bytes, sizeof bytes) || (bytes && bytes != arr[i].bytes))
