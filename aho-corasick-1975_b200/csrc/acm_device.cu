@@ -429,6 +429,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_stream_bytes = strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_smem_kb"))
     m->option_s2_smem_kb = strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
+  else if (!strcmp (key, "s2_dist_log2")) /* log2 of the largest distance table (in words) the stride-2 filter may use: default 23 = 32 MB */
+    m->option_s2_dist_log2 = strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "dfa_events")) /* 0: pass 2 of the DFA engines always walks the text again */
     m->option_no_events = !strtoull (value, 0, 10);
   else if (!strcmp (key, "s2_batches")) /* batches of 32 hits the stride-2 kernel confirms at a time: 1, 2 (default) or 3 */

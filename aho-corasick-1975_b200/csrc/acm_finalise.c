@@ -447,8 +447,12 @@ build_stride2 (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_optin)
       }
     }
     bl = calloc (b.words, sizeof (uint32_t));
+    /* distance table: 32 words per keyword while that stays at 16 MB (config 3), never more than that unless the table would be more
+     * than half full: it must stay L2-RESIDENT next to the streaming text -- at 64 MB (10^6 keywords, first version) every lookup
+     * was a DRAM access, 11.7 GB read for a 2 GiB text (profiles/r2_filter_scan_s2_c4s_2gib.txt) */
     uint32_t lg = 16;
-    while (lg < 24 && (1ull << lg) < 32ull * nk)
+    const uint32_t lg_cap = m->option_s2_dist_log2 ? (uint32_t)m->option_s2_dist_log2 : 23;
+    while (lg < 26 && ((lg < lg_cap && (1ull << lg) < 32ull * nk) || (1ull << lg) < 2ull * nk))
       lg++;
     t->s2_dist = calloc ((size_t)1 << lg, sizeof (uint32_t));
     t->kw_dist = malloc (((size_t)nk + 1) * sizeof (uint16_t));
