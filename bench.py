@@ -494,6 +494,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other configs (extra_configs) and the weak-scaling companion figure")
+    ap.add_argument("--with-c4", action="store_true", help="also run configs[3] sharded over the N GPUs (2 GiB per GPU); default at N = 8, its stated shape")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = dict(CONFIGS[args.config])
@@ -523,6 +524,14 @@ def main():
             weak = measure(args.config, cfg, args, ac75, torch, dist, rank, world, local, "weak", max(3, args.steps // 2), max(1, min(args.warmup, 2)), False, False, False, numa)
             if rank == 0:
                 line["weak"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "scaling", "matches_per_step", "kernel_ms")} | {"bytes_per_gpu": weak["config"]["bytes_per_gpu"]}
+        if world > 1 and args.config == "c3" and (world == 8 or args.with_c4):
+            # configs[3] as stated: 10^6 patterns over 16 GiB sharded across 8 GPUs (2 GiB per GPU; with --with-c4 at any N)
+            try:
+                c4 = measure("c4", dict(CONFIGS["c4"]), args, ac75, torch, dist, rank, world, local, "weak", max(3, args.steps // 2), max(1, min(args.warmup, 3)), False, False, True, numa)
+            except Exception as e:  # must not take the headline line with it (every rank fails or succeeds alike: same code, same sizes)
+                c4 = {"config": {"name": "c4"}, "error": f"{type(e).__name__}: {e}"}
+            if rank == 0:
+                line["extra_configs"] = [c4]
         if world == 1 and args.config == "c3":  # the other configs, driver-run in the same line
             extras = []
             for name in ("c2", "c4s", "c5"):
