@@ -678,7 +678,10 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
   p.q = t.q;
   p.lmax = t.lmax;
   const bool s2 = W == 1 && !dense && img->stride2; /* stride-2 kernel: its "tiles" for F2..F4 are spans of 2 KiB tiles */
-  p.tile_syms = s2 ? kS2SpanBytes : kRowsOpt * 512 / W;
+  /* dense mode stages every position of a tile (a stage as large as the tile): with 4-row tiles only 8 warps fit next to the filter
+   * (12 % occupancy, issue 11 %: profiles/README.md round 2), so the dense mode takes one-row tiles: all 32 warps for 32-bit symbols, 16 / 8 for 16-bit symbols / bytes (4 / 2 before) */
+  const bool one_row = dense;
+  p.tile_syms = s2 ? kS2SpanBytes : (one_row ? 1 : kRowsOpt) * 512 / W;
   p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
   p.bloom_s2 = img->d_bloom_s2.as<uint32_t> ();
   p.bloom_s2_words = t.bloom_s2_words;
@@ -747,7 +750,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
             : (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, false> : filter_scan_kernel<W, R_, Q_, K_, false, false>))
 #define ACM_F1(Q_, K_)                                                                                                                           \
   if (p.q == Q_ && K == K_)                                                                                                                      \
-    f1 = ACM_F1_ (Q_, K_, kRowsOpt)
+    f1 = one_row ? ACM_F1_ (Q_, K_, 1) : ACM_F1_ (Q_, K_, kRowsOpt)
   ACM_F1 (1, 2); ACM_F1 (2, 2);
   if (W == 1) {
     ACM_F1 (3, 2); ACM_F1 (4, 2);
