@@ -41,7 +41,7 @@ class Stats(ctypes.Structure):
                 ("last_nb_symbols", ctypes.c_uint64), ("last_nb_matches", ctypes.c_uint64), ("last_nb_candidates", ctypes.c_uint64),
                 ("main_kernel_launches", ctypes.c_uint64), ("total_kernel_launches", ctypes.c_uint64), ("fallback_count", ctypes.c_uint64), ("filter_fp", ctypes.c_double),
                 ("hot_spans", ctypes.c_uint64), ("dfa_event_scans", ctypes.c_uint64), ("filter_stride", ctypes.c_uint64),
-                ("dense_scans", ctypes.c_uint64), ("patch_count", ctypes.c_uint64), ("blob_loads", ctypes.c_uint64), ("dfa_tma_scans", ctypes.c_uint64)]
+                ("dense_scans", ctypes.c_uint64), ("patch_count", ctypes.c_uint64), ("blob_loads", ctypes.c_uint64), ("dfa_tma_scans", ctypes.c_uint64), ("dfa_lean_scans", ctypes.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

@@ -437,6 +437,8 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_s2_batches = strtoull (value, 0, 10);
   else if (!strcmp (key, "dfa_tma")) /* 0: the DFA count pass loads its chunks per thread instead of staging them through shared memory with TMA */
     m->option_no_tma = !strtoull (value, 0, 10);
+  else if (!strcmp (key, "dfa_lean")) /* 0: the TMA-staged count pass counts records itself instead of recording events only and counting from them */
+    m->option_no_lean = !strtoull (value, 0, 10);
   else if (!strcmp (key, "patch")) /* 0: every insertion between two scans rebuilds the tables (the in-place update is the default) */
     m->option_no_patch = !strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
@@ -600,14 +602,30 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uin
     g_error[0] = 0;
   }
   CUDA_TRY (cudaEventRecord (cx->ev[0], job.st));
+  /* lean pass 1: events only, records counted from the event lists afterwards.  Needs 2 x class in a byte, and event lists that do
+   * not cross a 4 GiB boundary (the kernel advances the low word of its event pointer only): lists of 2^k bytes aligned to their
+   * size, or a buffer that has no such boundary inside */
+  bool lean = false;
+  if (use_tma && use_events && p.K <= 128 && !m->option_no_lean) {
+    const uint64_t list_bytes = (uint64_t)p.events_per_chunk * 4, ev0 = (uint64_t)(uintptr_t)p.events, ev1 = ev0 + p.nchunks * list_bytes - 1;
+    lean = ((list_bytes & (list_bytes - 1)) == 0 && ev0 % list_bytes == 0) || (ev0 >> 32) == (ev1 >> 32);
+  }
   if (use_tma) {
-    void (*tma_k) (const DfaParams, const CUtensorMap) = use_events ? dfa_scan_tma_kernel<true> : dfa_scan_tma_kernel<false>;
+    void (*tma_k) (const DfaParams, const CUtensorMap) = lean ? dfa_scan_tma_lean_kernel : (use_events ? dfa_scan_tma_kernel<true> : dfa_scan_tma_kernel<false>);
     CUDA_TRY (cudaFuncSetAttribute (tma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
     const unsigned tgrid = (unsigned)std::min<uint64_t> ((p.tma_chunks + 1023) / 1024, (uint64_t)img->sm_count);
     tma_k<<<tgrid, 1024, tma_smem, job.st>>> (p, tmap);
     CUDA_TRY (cudaGetLastError ());
     cx->stats.total_kernel_launches += 1;
     cx->stats.dfa_tma_scans++;
+    if (lean) { /* records per chunk from the events just recorded */
+      DfaParams pc = p;
+      pc.nchunks = p.tma_chunks;
+      dfa_count_events_kernel<<<(unsigned)std::min<uint64_t> ((pc.nchunks + 7) / 8, (uint64_t)img->sm_count * 16), 256, 0, job.st>>> (pc);
+      CUDA_TRY (cudaGetLastError ());
+      cx->stats.total_kernel_launches += 1;
+      cx->stats.dfa_lean_scans++;
+    }
   }
   if (p.tma_chunks < p.nchunks) { /* everything, or the partial last chunk */
     p.first_chunk = p.tma_chunks;
@@ -626,8 +644,21 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uin
   *total = cx->h_small->grand_total;
   cx->stats.main_kernel_launches += 1;
   cx->stats.total_kernel_launches += 1;
-  if (use_events && cx->h_small->overflow)
+  if (use_events && cx->h_small->overflow) {
     use_events = false; /* a chunk met more output states than it has event slots: pass 2 walks */
+    if (lean) { /* ... and the counts taken from the truncated lists are wrong: counted again by walking */
+      void (*recount_k) (const DfaParams) = dfa_scan_kernel<Entry, kShared, false, false>;
+      CUDA_TRY (cudaFuncSetAttribute (recount_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)count_smem));
+      recount_k<<<grid, threads, count_smem, job.st>>> (p);
+      CUDA_TRY (cudaGetLastError ());
+      if ((rc = device_exclusive_scan (cx, p.chunk_counts, p.nchunks, cx->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))
+        return rc;
+      CUDA_TRY (cudaMemcpyAsync (&cx->h_small->grand_total, &d_small->grand_total, 8, cudaMemcpyDeviceToHost, job.st));
+      CUDA_TRY (cudaStreamSynchronize (job.st));
+      *total = cx->h_small->grand_total;
+      cx->stats.total_kernel_launches += 1;
+    }
+  }
 
   const uint64_t want = std::min<uint64_t> (*total, job.capacity);
   CUDA_TRY (cudaEventRecord (cx->ev[2], job.st));
@@ -973,6 +1004,7 @@ merge_stats (ACMB200Stats &into, const ACMB200Stats &scan) {
   into.dfa_event_scans += scan.dfa_event_scans;
   into.dense_scans += scan.dense_scans;
   into.dfa_tma_scans += scan.dfa_tma_scans;
+  into.dfa_lean_scans += scan.dfa_lean_scans;
 }
 
 static int

@@ -426,6 +426,162 @@ dfa_scan_tma_kernel (const __grid_constant__ DfaParams p, const __grid_constant_
   }
 }
 
+/* Lean form of the TMA-staged pass 1 (the usual pass 1 of `dfa_smem` when events are recorded): the walk records its events and
+ * nothing else.  The records of a chunk are counted afterwards from its event list (dfa_count_events_kernel), so the per-byte
+ * work loses the third shared-memory lookup (records per state), the index clamp and the add: 9 instructions per byte instead
+ * of 22 --
+ *   PRMT (byte), LDS.U8 (2 x class), IMAD (row address), LDS.U16 (next state), IMAD (event word), IADD (position), ISETP,
+ *   and under the predicate one STG and one 32-bit pointer increment.
+ * The tricks: the class table holds 2 x class and the row stride is 2 K bytes, so one IMAD yields the byte address of the next
+ * delta entry; the tables are addressed as [register + uniform base + immediate]; the event pointer is a 32-bit low word next to
+ * a constant high word (the host guarantees that a chunk's event list does not cross a 4 GiB boundary), so a recorded event
+ * advances it with ONE predicated add; the event word (output state index << 16 | position) is state * 65536 + a running
+ * position that already carries -threshold << 16. */
+__global__ void __launch_bounds__ (1024, 1)
+dfa_scan_tma_lean_kernel (const __grid_constant__ DfaParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__ (128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *stage_buf = smem + (size_t)warp * kTmaWarpBytes;
+  uint64_t *mbar = reinterpret_cast<uint64_t *> (smem + 32 * kTmaWarpBytes) + 2 * warp;
+  uint8_t *s_class2 = smem + kTmaCtaBytes;
+  const unsigned char *s_delta8 = smem + kTmaCtaBytes + 256;
+  const size_t delta_bytes = ((size_t)p.nb_states * p.K * 2 + 15) / 16 * 16;
+  if (lane == 0) {
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32 (&mbar[0])));
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32 (&mbar[1])));
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    s_class2[i] = (uint8_t)(2u * p.class_of_byte[i]); /* the host takes this kernel only while 2 (K - 1) fits a byte */
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *> (p.delta);
+    uint4 *dst = reinterpret_cast<uint4 *> (smem + kTmaCtaBytes + 256);
+    for (uint32_t i = threadIdx.x; i < delta_bytes / 16; i += blockDim.x)
+      dst[i] = src[i];
+  }
+  __syncthreads ();
+
+  const uint32_t K2 = 2u * p.K, thr = p.out_threshold;
+  const uint32_t chunk = (uint32_t)p.chunk, warm_pad = (p.warm + kTmaStageBytes - 1) / kTmaStageBytes * kTmaStageBytes;
+  const uint32_t warm_stages = warm_pad / kTmaStageBytes, stages = warm_stages + chunk / kTmaStageBytes;
+  const uint32_t ev_cap4 = p.events_per_chunk * 4u;
+  uint32_t g = 0;
+  auto issue = [&] (uint32_t k, uint64_t row0, uint32_t slot) {
+    if (lane == 0) {
+      const int32_t x = k < warm_stages ? (int32_t)(chunk - warm_pad + k * kTmaStageBytes) : (int32_t)((k - warm_stages) * kTmaStageBytes);
+      const int32_t y = (int32_t)row0 - (k < warm_stages ? 1 : 0);
+      const uint32_t bar = smem_u32 (&mbar[slot]), dst = smem_u32 (stage_buf + slot * 32 * kTmaStageBytes);
+      asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(32u * kTmaStageBytes) : "memory");
+      asm volatile ("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(&tmap), "r"(bar), "r"(x), "r"(y)
+                    : "memory");
+    }
+  };
+  /* the two tables by their shared-space addresses, held in uniform registers (a warp reduction is how a value gets there):
+   * the lookups are LDS [register + uniform register], no address add per byte */
+  const uint32_t class_base = __reduce_max_sync (kFull, smem_u32 (s_class2)), delta_base = __reduce_max_sync (kFull, smem_u32 (s_delta8));
+  auto next_state = [&] (uint32_t state, uint32_t word, int b) -> uint32_t {
+    uint32_t c2, next, at;
+    asm ("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(__byte_perm (word, 0u, 0x4440 + b) + class_base));
+    asm ("mad.lo.u32 %0, %1, %2, %3;" : "=r"(at) : "r"(state), "r"(K2), "r"(c2)); /* opaque: ONE multiply-add on the state -> state chain */
+    asm ("ld.shared.u16 %0, [%1];" : "=r"(next) : "r"(at + delta_base));
+    return next;
+  };
+
+  for (uint64_t row0 = ((uint64_t)blockIdx.x * 32 + warp) * 32; row0 < p.tma_chunks; row0 += (uint64_t)gridDim.x * 32 * 32) {
+    const uint64_t c = row0 + lane;
+    const bool have = c < p.tma_chunks; /* rows beyond the tensor read as zeros and are not reported */
+    const uint64_t start = c * p.chunk;
+    uint32_t state = c == 0 ? p.init_state : 0;
+    const int32_t report_rel = have ? (int32_t)min (p.lead > start ? p.lead - start : (uint64_t)0, p.chunk) : (int32_t)chunk;
+    uint64_t ev_ptr = reinterpret_cast<uint64_t> (p.events + c * p.events_per_chunk); /* only its low word ever changes */
+    const uint32_t ev_lo0 = (uint32_t)ev_ptr;
+    uint32_t dropped = 0; /* events met while the list was full (then pass 2 walks the text instead) */
+#define ev_lo ((uint32_t)ev_ptr)
+
+    issue (0, row0, g & 1);
+    if (stages > 1)
+      issue (1, row0, (g + 1) & 1);
+    for (uint32_t k = 0; k < stages; k++, g++) {
+      const uint32_t slot = g & 1, phase = (g >> 1) & 1;
+      {
+        const uint32_t bar = smem_u32 (&mbar[slot]);
+        uint32_t done = 0;
+        while (!done)
+          asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+      }
+      const uint4 *row = reinterpret_cast<const uint4 *> (stage_buf + slot * 32 * kTmaStageBytes + lane * kTmaStageBytes);
+      const uint4 va = row[0], vb = row[1];
+      asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); /* this lane's reads before the refill (see dfa_scan_tma_kernel) */
+      __syncwarp ();
+      if (k + 2 < stages)
+        issue (k + 2, row0, slot);
+      const uint32_t w[8] = { va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w };
+      if (k < warm_stages) { /* warm-up: walked, never reported */
+        if (c != 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            state = next_state (state, w[i >> 2], i & 3);
+        }
+      } else {
+        const int32_t rel0 = (int32_t)((k - warm_stages) * kTmaStageBytes);
+        if (rel0 >= report_rel && (ev_lo - ev_lo0) + 32u * 4u <= ev_cap4) {
+          /* usual stage: every byte reportable, room for 32 more events: straight-line, one predicated store per byte */
+          uint32_t relc = (uint32_t)rel0 - (thr << 16);
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            state = next_state (state, w[i >> 2], i & 3);
+            const uint32_t val = state * 65536u + relc; /* (state - thr) << 16 | position */
+            relc++;
+            asm volatile ("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\tsetp.ge.u32 p, %1, %2;\n\t@p st.global.u32 [%0], %3;\n\tmov.b64 {lo, hi}, %0;\n\t@p add.u32 lo, lo, 4;\n\tmov.b64 %0, {lo, hi};\n\t}"
+                          : "+l"(ev_ptr)
+                          : "r"(state), "r"(thr), "r"(val)
+                          : "memory");
+          }
+        } else { /* the stage that holds the caller's lead, or a nearly full event list: per-byte tests */
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            state = next_state (state, w[i >> 2], i & 3);
+            if (state >= thr && rel0 + i >= report_rel) {
+              if (ev_lo - ev_lo0 < ev_cap4) {
+                *reinterpret_cast<uint32_t *> (ev_ptr) = (uint32_t)(rel0 + i) | ((state - thr) << 16);
+                ev_ptr += 4; /* no carry: the list does not cross a 4 GiB boundary */
+              } else
+                dropped++;
+            }
+          }
+        }
+      }
+    }
+    if (have) {
+      p.chunk_events[c] = (ev_lo - ev_lo0) / 4u + dropped;
+      if (dropped)
+        atomicExch (p.events_overflow, 1u);
+    }
+#undef ev_lo
+    __syncwarp ();
+  }
+}
+
+/* Records per chunk from the recorded events (after the lean pass 1): a warp per chunk sums the sizes of the output sets of the
+ * chunk's events.  A chunk whose list overflowed has set *events_overflow: the host then counts by walking. */
+__global__ void __launch_bounds__ (256)
+dfa_count_events_kernel (const __grid_constant__ DfaParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t c = warp_global; c < p.nchunks; c += nwarps) {
+    const uint32_t nev = min (p.chunk_events[c], p.events_per_chunk);
+    const uint32_t *ev = p.events + c * p.events_per_chunk;
+    uint32_t sum = 0;
+    for (uint32_t i = lane; i < nev; i += 32) {
+      const uint32_t o = ev[i] >> 16;
+      sum += p.out_offsets[o + 1] - p.out_offsets[o];
+    }
+    sum = __reduce_add_sync (kFull, sum);
+    if (lane == 0)
+      p.chunk_counts[c] = sum;
+  }
+}
+
 /* Pass 2 of the shared-memory DFA engine when pass 1 recorded its events: no walk, no table.  A warp takes one chunk at a time and
  * expands 32 of its events per step: records per event from the CSR offsets, a warp scan for the positions, and stores that are
  * contiguous across the warp (the records of a chunk are contiguous in the output, in position order, longest keyword first). */
@@ -1118,6 +1274,92 @@ s2_probe (const FilterParams &p, const uint8_t *text8, uint64_t s, F &&emit) {
   }
 }
 
+/* End of a span of the stride-2 kernels: the span's candidates (cands[], any order) are sorted by end position, equal ends merged,
+ * and appended to the candidate list with one reservation; a span whose stages overflowed (hot) is listed for
+ * filter_hot_spans_kernel instead. */
+__device__ __forceinline__ void
+s2_finish_span (const FilterParams &p, uint32_t span, uint64_t span_base, uint32_t *cands, uint32_t ncand, bool hot, int lane) {
+  /* ---- the span's candidates: sorted by end position, equal ends merged (their distance masks OR-ed) ---- */
+  uint32_t nspill = 0;
+  if (hot) { /* rare */
+    ncand = 0;
+    if (lane == 0) {
+      const unsigned int at = atomicAdd (p.hot_count, 1u);
+      if (at < p.hot_cap)
+        p.hot_spans[at] = (uint32_t)span;
+    }
+  } else if (ncand) {
+    uint32_t val[2], dm[2], rank[2] = { 0, 0 };
+    bool first[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint32_t i = lane + 32 * r;
+      first[r] = i < ncand;
+      val[r] = first[r] ? cands[i] : 0xFFFFFFFFu;
+      dm[r] = val[r] & ACM_S2_DMASK_ALL;
+    }
+    if (ncand > 1) {
+      for (uint32_t j = 0; j < ncand; j++) {
+        const uint32_t w = cands[j];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          if ((w >> 15) == (val[r] >> 15)) {
+            dm[r] |= w & ACM_S2_DMASK_ALL;
+            if (j < (uint32_t)lane + 32 * r)
+              first[r] = false; /* an earlier entry with the same end represents it */
+          }
+      }
+      const uint32_t f0 = __ballot_sync (kFull, first[0]), f1 = __ballot_sync (kFull, first[1]);
+      for (uint32_t j = 0; j < ncand; j++)
+        if (((j < 32 ? f0 >> j : f1 >> (j - 32)) & 1u)) {
+          const uint32_t w = cands[j];
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            rank[r] += (w >> 15) < (val[r] >> 15);
+        }
+      __syncwarp ();
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        if (first[r])
+          cands[rank[r]] = (val[r] & ~ACM_S2_DMASK_ALL) | dm[r];
+      ncand = __popc (f0) + __popc (f1);
+      __syncwarp ();
+    }
+    /* ends beyond the span (at most kS2EndSlack bytes into the next one) come last */
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint32_t i = lane + 32 * r;
+      nspill += __popc (__ballot_sync (kFull, i < ncand && (cands[i] >> 15) >= kS2SpanBytes));
+    }
+  }
+
+  /* ---- one reservation per span ---- */
+  uint64_t first_slot = 0;
+  if (ncand) {
+    unsigned long long seg = 0;
+    if (lane == 0)
+      seg = atomicAdd (p.cand_count, (unsigned long long)ncand);
+    seg = __shfl_sync (kFull, seg, 0);
+    if (seg + ncand > p.cand_cap) {
+      if (lane == 0)
+        atomicExch (p.overflow, 1u);
+      ncand = nspill = 0;
+    } else {
+      first_slot = seg;
+      for (uint32_t i = lane; i < ncand; i += 32) {
+        const uint32_t c = cands[i];
+        p.cand_pos[seg + i] = (span_base + (c >> 15)) | ((uint64_t)(c & ACM_S2_DMASK_ALL) << 48);
+      }
+    }
+  }
+  if (lane == 0) {
+    p.tile_first[span] = first_slot;
+    p.tile_n[span] = ncand;
+    p.tile_spill[span] = nspill;
+  }
+  __syncwarp ();
+}
+
 template <int K, int kBatches, int kRows>
 __global__ void __launch_bounds__ (1024, 1)
 filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
@@ -1406,86 +1648,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
         hot = true;
     }
 
-    /* ---- the span's candidates: sorted by end position, equal ends merged (their distance masks OR-ed) ---- */
-    uint32_t nspill = 0;
-    if (hot) { /* rare */
-      ncand = 0;
-      if (lane == 0) {
-        const unsigned int at = atomicAdd (p.hot_count, 1u);
-        if (at < p.hot_cap)
-          p.hot_spans[at] = (uint32_t)span;
-      }
-    } else if (ncand) {
-      uint32_t val[2], dm[2], rank[2] = { 0, 0 };
-      bool first[2];
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const uint32_t i = lane + 32 * r;
-        first[r] = i < ncand;
-        val[r] = first[r] ? cands[i] : 0xFFFFFFFFu;
-        dm[r] = val[r] & ACM_S2_DMASK_ALL;
-      }
-      if (ncand > 1) {
-        for (uint32_t j = 0; j < ncand; j++) {
-          const uint32_t w = cands[j];
-#pragma unroll
-          for (int r = 0; r < 2; r++)
-            if ((w >> 15) == (val[r] >> 15)) {
-              dm[r] |= w & ACM_S2_DMASK_ALL;
-              if (j < (uint32_t)lane + 32 * r)
-                first[r] = false; /* an earlier entry with the same end represents it */
-            }
-        }
-        const uint32_t f0 = __ballot_sync (kFull, first[0]), f1 = __ballot_sync (kFull, first[1]);
-        for (uint32_t j = 0; j < ncand; j++)
-          if (((j < 32 ? f0 >> j : f1 >> (j - 32)) & 1u)) {
-            const uint32_t w = cands[j];
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-              rank[r] += (w >> 15) < (val[r] >> 15);
-          }
-        __syncwarp ();
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-          if (first[r])
-            cands[rank[r]] = (val[r] & ~ACM_S2_DMASK_ALL) | dm[r];
-        ncand = __popc (f0) + __popc (f1);
-        __syncwarp ();
-      }
-      /* ends beyond the span (at most kS2EndSlack bytes into the next one) come last */
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const uint32_t i = lane + 32 * r;
-        nspill += __popc (__ballot_sync (kFull, i < ncand && (cands[i] >> 15) >= kS2SpanBytes));
-      }
-    }
-
-    /* ---- one reservation per span ---- */
-    uint64_t first_slot = 0;
-    if (ncand) {
-      unsigned long long seg = 0;
-      if (lane == 0)
-        seg = atomicAdd (p.cand_count, (unsigned long long)ncand);
-      seg = __shfl_sync (kFull, seg, 0);
-      if (seg + ncand > p.cand_cap) {
-        if (lane == 0)
-          atomicExch (p.overflow, 1u);
-        ncand = nspill = 0;
-      } else {
-        first_slot = seg;
-        const uint64_t span_base = tile0 * kTileBytes;
-        for (uint32_t i = lane; i < ncand; i += 32) {
-          const uint32_t c = cands[i];
-          p.cand_pos[seg + i] = (span_base + (c >> 15)) | ((uint64_t)(c & ACM_S2_DMASK_ALL) << 48);
-        }
-      }
-    }
-    if (lane == 0) {
-      p.tile_first[span] = first_slot;
-      p.tile_n[span] = ncand;
-      p.tile_spill[span] = nspill;
-    }
-    __syncwarp ();
+    s2_finish_span (p, span, tile0 * kTileBytes, cands, ncand, hot, lane);
   }
 }
 

@@ -88,6 +88,7 @@ typedef struct {
   uint64_t patch_count;     /* finalises that patched the resident tables in place instead of rebuilding them (append-only insertions) */
   uint64_t blob_loads;      /* finalises that uploaded the tables of a blob (acm_b200_load) as they were */
   uint64_t dfa_tma_scans;   /* DFA scans whose count pass staged the text through shared memory with TMA (since creation) */
+  uint64_t dfa_lean_scans;  /* ... of which: the count pass recorded events only and the records were counted from the event lists */
 } ACMB200Stats;
 
 /* Number of CUDA devices visible (0 if none / no driver). */
