@@ -18,7 +18,7 @@
 #include <string.h>
 
 #define ACM_BLOB_MAGIC 0x424F4C4235374341ull /* "AC75BLOB" */
-#define ACM_BLOB_VERSION 2u
+#define ACM_BLOB_VERSION 3u
 
 struct blob_header {
   uint64_t magic;

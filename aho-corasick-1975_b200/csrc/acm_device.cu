@@ -820,7 +820,10 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
   const unsigned vgrid = (unsigned)std::min<uint64_t> ((p.cand_cap + 255) / 256, (uint64_t)img->sm_count * 8), tgrid = (unsigned)((p.ntiles + 255) / 256);
   filter_verify_kernel<W, false><<<vgrid, 256, 0, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
-  filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
+  if (dense && !s2) /* tens of candidates per tile: one warp per tile */
+    filter_tile_totals_dense_kernel<<<(unsigned)std::min<uint64_t> ((p.ntiles + 7) / 8, (uint64_t)img->sm_count * 64), 256, 0, job.st>>> (p);
+  else
+    filter_tile_totals_kernel<<<tgrid, 256, 0, job.st>>> (p);
   CUDA_TRY (cudaGetLastError ());
   cx->stats.total_kernel_launches += 2;
   if ((rc = device_exclusive_scan (cx, p.tile_matches, p.ntiles, cx->d_offsets.as<uint64_t> (), &d_small->grand_total, job.st)))

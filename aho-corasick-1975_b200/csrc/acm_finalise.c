@@ -629,7 +629,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
       if (depth[from] >= q && count[from] >= 2)
         kept++;
     }
-  t->edge_slots = pow2_at_least (2 * kept + 16);
+  t->edge_slots = pow2_at_least (3 * kept + 16);
   t->edges = malloc (t->edge_slots * sizeof (acm_slot));
   if (!t->edges)
     goto done;
@@ -645,7 +645,7 @@ build_filter (struct _ac_machine *m, struct acm_tables *t, uint64_t smem_budget,
       }
     }
   /* exact q-gram table: depth-q node (or tail), and the keyword of exactly q symbols ending there */
-  t->qgram_slots = pow2_at_least (2 * nq + 16);
+  t->qgram_slots = pow2_at_least (3 * nq + 16);
   t->qgrams = malloc (t->qgram_slots * sizeof (acm_slot));
   if (!t->qgrams)
     goto done;

@@ -1800,21 +1800,38 @@ filter_verify_kernel (const __grid_constant__ FilterParams p) {
             int64_t e = pos - (int64_t)len, wi = e >> 2;
             const uint32_t sh = ((uint32_t)(e & 3) + 1u) * 8u;
             uint32_t hi = tw[wi];
-            for (uint32_t j = len; j < klen && same; j += 4, wi--) {
-              const uint32_t lo = wi > 0 ? tw[wi - 1] : 0u;
-              const uint32_t t_rev = __byte_perm (__funnelshift_rc (lo, hi, sh), 0u, 0x0123); /* lowest byte = text byte e */
-              const uint32_t rem = klen - j, mask = rem >= 4 ? 0xFFFFFFFFu : (1u << (8 * rem)) - 1u;
-              same = ((t_rev ^ __ldg (rp + (j >> 2))) & mask) == 0;
-              hi = lo;
+            for (uint32_t j = len; j < klen && same; j += 8, wi -= 2) { /* two steps per round: their four loads are in flight together */
+              const bool two = j + 4 < klen;
+              const uint32_t lo1 = wi > 0 ? tw[wi - 1] : 0u, lo2 = two && wi > 1 ? tw[wi - 2] : 0u;
+              const uint32_t r1 = __ldg (rp + (j >> 2)), r2 = two ? __ldg (rp + (j >> 2) + 1) : 0u;
+              const uint32_t t1 = __byte_perm (__funnelshift_rc (lo1, hi, sh), 0u, 0x0123); /* lowest byte = text byte e */
+              const uint32_t t2 = __byte_perm (__funnelshift_rc (lo2, lo1, sh), 0u, 0x0123);
+              const uint32_t rem = klen - j, m1 = rem >= 4 ? 0xFFFFFFFFu : (1u << (8 * rem)) - 1u;
+              const uint32_t m2 = !two ? 0u : (rem >= 8 ? 0xFFFFFFFFu : (1u << (8 * (rem - 4))) - 1u);
+              same = (((t1 ^ r1) & m1) | ((t2 ^ r2) & m2)) == 0;
+              hi = lo2;
             }
           }
         } else {
           klen = p.kw_len[k];
           const typename SymT<W>::type *kwsym = reinterpret_cast<const typename SymT<W>::type *> (p.kw_pool) + p.kw_off[k];
-          for (uint32_t j = len; j < klen && same; j++) {
-            uint32_t sym;
-            same = symbol_at<W> (p, pos - (int64_t)j, &sym) && sym == kwsym[klen - 1 - j];
-          }
+          if ((uint64_t)pos + 1 >= klen) {
+            /* the keyword lies inside the text: four symbols per step, all eight loads of a step issued before the first
+             * compare (one symbol per step was one L2 round trip per symbol) */
+            const typename SymT<W>::type *tx = reinterpret_cast<const typename SymT<W>::type *> (p.text) + pos;
+            for (uint32_t j = len; j < klen && same; j += 4) {
+              uint32_t diff = 0;
+#pragma unroll
+              for (uint32_t u = 0; u < 4; u++)
+                if (j + u < klen)
+                  diff |= (uint32_t)*(tx - (int64_t)(j + u)) ^ (uint32_t)kwsym[klen - 1 - j - u];
+              same = diff == 0;
+            }
+          } else
+            for (uint32_t j = len; j < klen && same; j++) {
+              uint32_t sym;
+              same = symbol_at<W> (p, pos - (int64_t)j, &sym) && sym == kwsym[klen - 1 - j];
+            }
         }
         if (same)
           report (k, klen);
@@ -1863,6 +1880,35 @@ filter_tile_totals_kernel (const __grid_constant__ FilterParams p) {
     total += p.cand_matches[c];
   }
   p.tile_matches[tile] = total;
+}
+
+/* F3 of the dense mode (no spill lists, tens of candidates per tile): one WARP per tile, 32 candidates per step, coalesced; the
+ * thread-per-tile kernel above walked each tile's list serially (0.22 ms of a 1.5 ms config-5 step). */
+__global__ void __launch_bounds__ (256)
+filter_tile_totals_dense_kernel (const __grid_constant__ FilterParams p) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < p.ntiles; tile += nwarps) {
+    const uint32_t n = p.tile_n[tile];
+    const uint64_t first = p.tile_first[tile];
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < n; i += 32) {
+      const bool have = i + lane < n;
+      const uint32_t v = have ? p.cand_matches[first + i + lane] : 0u;
+      uint32_t incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync (kFull, incl, d);
+        if (lane >= d)
+          incl += o;
+      }
+      if (have)
+        p.cand_prefix[first + i + lane] = total + incl - v;
+      total += __shfl_sync (kFull, incl, 31);
+    }
+    if (lane == 0)
+      p.tile_matches[tile] = total;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------------------------ */

@@ -12,15 +12,18 @@
 #define ACM_HD static inline
 #endif
 
-/* 64-bit finaliser (splitmix64) for the open-addressing tables living in global memory. */
+/* Hash of the open-addressing tables living in global memory (q-gram -> node, reverse-trie edges; callers mask it with
+ * slots - 1): the top half of key * 2^64/phi, byte-swapped so that the best-mixed bits of the product -- its top ones -- are the
+ * low ones.  Four instructions on the GPU (IMAD.WIDE + 2 IMAD + PRMT); the splitmix64 finaliser used before cost 21, a tenth of
+ * all instructions of the verification kernel (profiles/r4_verify_c5.txt). */
 ACM_HD uint64_t
 acm_mix64 (uint64_t x) {
-  x ^= x >> 30;
-  x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27;
-  x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return x;
+  const uint32_t top = (uint32_t)((x * 0x9E3779B97F4A7C15ull) >> 32);
+#if defined(__CUDA_ARCH__)
+  return __byte_perm (top, 0u, 0x0123);
+#else
+  return __builtin_bswap32 (top);
+#endif
 }
 
 /* q-gram key -> 32-bit value fed to the shared-memory filter hashes (identity for keys that fit 32 bits). */
