@@ -710,9 +710,10 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
   p.lmax = t.lmax;
   const bool s2 = W == 1 && !dense && img->stride2; /* stride-2 kernel: its "tiles" for F2..F4 are spans of 2 KiB tiles */
   /* dense mode stages every position of a tile (a stage as large as the tile): with 4-row tiles only 8 warps fit next to the filter
-   * (12 % occupancy, issue 11 %: profiles/README.md round 2), so the dense mode takes one-row tiles: all 32 warps for 32-bit symbols, 16 / 8 for 16-bit symbols / bytes (4 / 2 before) */
-  const bool one_row = dense;
-  p.tile_syms = s2 ? kS2SpanBytes : (one_row ? 1 : kRowsOpt) * 512 / W;
+   * (12 % occupancy, issue 11 %: profiles/README.md round 2), so the dense mode takes small tiles with byte-sized stage entries where
+   * they suffice: all 32 warps for 32- and 16-bit symbols, 8 for bytes */
+  constexpr int kDenseRows = W == 4 ? 2 : 1; /* 256 / 256 / 512 symbols per dense tile for 32- / 16- / 8-bit symbols; up to 256 the stage entries are bytes */
+  p.tile_syms = s2 ? kS2SpanBytes : (dense ? kDenseRows : kRowsOpt) * 512 / W;
   p.ntiles = (job.n + p.tile_syms - 1) / p.tile_syms;
   p.bloom_s2 = img->d_bloom_s2.as<uint32_t> ();
   p.bloom_s2_words = t.bloom_s2_words;
@@ -747,7 +748,7 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
   /* candidate list (32 bytes of scratch per entry): every position in dense mode; otherwise what the caller expects from the
    * candidate rate it has seen (run_filter) -- a denser text overflows it and is redone with a larger list or in dense mode */
   p.cand_cap = dense ? job.n : std::min<uint64_t> (job.n, sparse_cand_cap);
-  size_t stage_bytes_per_warp = (size_t)p.stage_cap * 2 + 16; /* 16-bit positions + the warp's counter */
+  size_t stage_bytes_per_warp = (size_t)p.stage_cap * (dense && p.tile_syms <= 256 ? 1 : 2) + 16; /* 16- or 8-bit positions (StageT of the kernel) + the warp's counter */
   int warps = 32;
   while (warps > 1 && (size_t)t.bloom_words * 4 + warps * stage_bytes_per_warp > img->smem_optin - 1024)
     warps /= 2;
@@ -776,12 +777,10 @@ run_filter_once (ACMachine *m, acm_device_image *img, ScanContext *cx, const Sca
   void (*f1) (const FilterParams) = nullptr;
   const bool ordered = dense; /* dense mode stages in position order (warp scan); the usual mode stages unordered and sorts the few survivors */
   const int K = 2; /* bits per key; 3 was measured slower, the kernels keep K as a template parameter */
-#define ACM_F1_(Q_, K_, R_)                                                                                                                      \
-  (p.bloom2 ? (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, true> : filter_scan_kernel<W, R_, Q_, K_, false, true>)       \
-            : (ordered ? filter_scan_kernel<W, R_, Q_, K_, true, false> : filter_scan_kernel<W, R_, Q_, K_, false, false>))
+#define ACM_F1_(Q_, K_, R_, O_) (p.bloom2 ? filter_scan_kernel<W, R_, Q_, K_, O_, true> : filter_scan_kernel<W, R_, Q_, K_, O_, false>)
 #define ACM_F1(Q_, K_)                                                                                                                           \
   if (p.q == Q_ && K == K_)                                                                                                                      \
-    f1 = one_row ? ACM_F1_ (Q_, K_, 1) : ACM_F1_ (Q_, K_, kRowsOpt)
+    f1 = ordered ? ACM_F1_ (Q_, K_, kDenseRows, true) : ACM_F1_ (Q_, K_, kRowsOpt, false)
   ACM_F1 (1, 2); ACM_F1 (2, 2);
   if (W == 1) {
     ACM_F1 (3, 2); ACM_F1 (4, 2);

@@ -979,12 +979,15 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
-  /* per warp: a 16-byte header (hit counter) then stage_cap 16-bit tile-relative positions */
-  uint32_t *stage_count = reinterpret_cast<uint32_t *> (s_stage_all + (size_t)warp * (p.stage_cap * 2 + 16));
-  uint16_t *stage = reinterpret_cast<uint16_t *> (stage_count + 4);
   constexpr int kSyms = 16 / W;        /* symbols per lane per row */
   constexpr int kRowSyms = 32 * kSyms; /* symbols per row */
   constexpr uint32_t kTileSyms = kRows * kRowSyms; /* symbols per tile: kRows loads in flight per lane */
+  /* per warp: a 16-byte header (hit counter) then stage_cap tile-relative positions -- 16 bits each, 8 in the dense mode when a
+   * tile has at most 256 symbols (its stage holds EVERY position of a tile: with bytes, two rows of 32-bit symbols take the room
+   * of one, and the fixed costs of a tile are spread over twice the text) */
+  typedef typename std::conditional<(kOrdered && kTileSyms <= 256), uint8_t, uint16_t>::type StageT;
+  uint32_t *stage_count = reinterpret_cast<uint32_t *> (s_stage_all + (size_t)warp * (p.stage_cap * sizeof (StageT) + 16));
+  StageT *stage = reinterpret_cast<StageT *> (stage_count + 4);
   constexpr uint32_t q = Q;
   const uint32_t nwords = p.bloom_words, stage_cap = p.stage_cap;
   const uint64_t first_valid = max (p.lead, (uint64_t)(q - 1)); /* windows that start before the text are handled below */
@@ -1044,7 +1047,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         for (uint64_t pos = p.lead; pos < min ((uint64_t)(q - 1), p.n); pos++) {
           uint64_t key;
           if (qgram_key_at<W> (p, (int64_t)pos, &key) && staged < stage_cap)
-            stage[staged++] = (uint16_t)pos; /* confirmed below like any other staged hit */
+            stage[staged++] = (StageT)pos; /* confirmed below like any other staged hit */
         }
       staged = __shfl_sync (kFull, staged, 0);
     }
@@ -1102,7 +1105,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
           const int i = __ffs (h) - 1;
           h &= h - 1;
           if (at < stage_cap)
-            stage[at] = (uint16_t)(rel0 + i);
+            stage[at] = (StageT)(rel0 + i);
           at++;
         }
         row_start += total;
@@ -1125,7 +1128,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
             const int i = __ffs (h) - 1;
             h &= h - 1;
             if (at < stage_cap)
-              stage[at] = (uint16_t)(rel0 + i);
+              stage[at] = (StageT)(rel0 + i);
             at++;
           }
         }
@@ -1179,7 +1182,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
       for (int u = 0; u < 2; u++) {
         const uint32_t mask = __ballot_sync (kFull, ok[u]);
         if (ok[u])
-          stage[kept + __popc (mask & lanes_below)] = (uint16_t)rel[u];
+          stage[kept + __popc (mask & lanes_below)] = (StageT)rel[u];
         kept += __popc (mask);
       }
       __syncwarp ();
@@ -1200,10 +1203,10 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
         /* positions are distinct, so ranks are a permutation; write through a second pass to avoid overwriting unread entries */
         if (b + 32 >= kept && b == 0) {
           if (i < kept)
-            stage[rank] = (uint16_t)mine;
+            stage[rank] = (StageT)mine;
         } else { /* more than 32 survivors: use the upper half of the stage as scratch */
           if (i < kept)
-            stage[stage_cap / 2 + rank] = (uint16_t)mine;
+            stage[stage_cap / 2 + rank] = (StageT)mine;
         }
         __syncwarp ();
       }
@@ -1736,15 +1739,17 @@ __global__ void __launch_bounds__ (256)
 filter_verify_kernel (const __grid_constant__ FilterParams p) {
   const uint64_t nb_candidates = min ((uint64_t)*p.cand_count, p.cand_cap);
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nb_candidates; c += (uint64_t)gridDim.x * blockDim.x) {
-  const uint64_t packed = p.cand_pos[c];
-  const int64_t pos = (int64_t)(packed & ACM_CAND_POS_MASK);
-  const uint32_t dmask = (uint32_t)(packed >> 48); /* 0: every keyword ending here is reported */
   uint32_t expected = 0;
   uint64_t out = 0;
-  if (kEmit) {
+  if (kEmit) { /* a candidate without matches costs F4 this one load */
     expected = p.cand_matches[c];
     if (!expected)
       continue;
+  }
+  const uint64_t packed = p.cand_pos[c];
+  const int64_t pos = (int64_t)(packed & ACM_CAND_POS_MASK);
+  const uint32_t dmask = (uint32_t)(packed >> 48); /* 0: every keyword ending here is reported */
+  if (kEmit) {
     const uint64_t tile = (uint64_t)pos / p.tile_syms;
     out = p.tile_offsets[tile] + p.cand_prefix[c];
     if (expected <= 2) { /* usual case: the counting pass kept them, no second walk */
@@ -1891,10 +1896,11 @@ filter_tile_totals_dense_kernel (const __grid_constant__ FilterParams p) {
   for (uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < p.ntiles; tile += nwarps) {
     const uint32_t n = p.tile_n[tile];
     const uint64_t first = p.tile_first[tile];
-    uint32_t total = 0;
+    uint32_t total = 0, v_next = (uint32_t)lane < n ? p.cand_matches[first + lane] : 0u;
     for (uint32_t i = 0; i < n; i += 32) {
       const bool have = i + lane < n;
-      const uint32_t v = have ? p.cand_matches[first + i + lane] : 0u;
+      const uint32_t v = v_next;
+      v_next = i + 32 + lane < n ? p.cand_matches[first + i + 32 + lane] : 0u; /* in flight during the scan below */
       uint32_t incl = v;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
