@@ -437,8 +437,9 @@ acm_b200_set_option (ACMachine *m, const char *key, const char *value) {
     m->option_s2_batches = strtoull (value, 0, 10);
   else if (!strcmp (key, "dfa_tma")) /* 0: the DFA count pass loads its chunks per thread instead of staging them through shared memory with TMA */
     m->option_no_tma = !strtoull (value, 0, 10);
-  else if (!strcmp (key, "dfa_lean")) /* 0: the TMA-staged count pass counts records itself instead of recording events only and counting from them */
-    m->option_no_lean = !strtoull (value, 0, 10);
+  else if (!strcmp (key, "dfa_lean")) /* 1: the TMA-staged count pass records events only and the records are counted from the event lists afterwards
+                                        * (default 0: it counts them itself -- the two forms measured within 3 % of each other, either way round, on different boxes) */
+    m->option_lean = strtoull (value, 0, 10) != 0;
   else if (!strcmp (key, "patch")) /* 0: every insertion between two scans rebuilds the tables (the in-place update is the default) */
     m->option_no_patch = !strtoull (value, 0, 10), m->generation++, m->force_rebuild = 1;
   else if (!strcmp (key, "stride2")) /* 0: keep the one-test-per-position filter kernel even where the stride-2 one applies */
@@ -606,7 +607,7 @@ run_dfa (ACMachine *m, acm_device_image *img, ScanContext *cx, ScanJob &job, uin
    * not cross a 4 GiB boundary (the kernel advances the low word of its event pointer only): lists of 2^k bytes aligned to their
    * size, or a buffer that has no such boundary inside */
   bool lean = false;
-  if (use_tma && use_events && p.K <= 128 && !m->option_no_lean) {
+  if (use_tma && use_events && p.K <= 128 && m->option_lean) {
     const uint64_t list_bytes = (uint64_t)p.events_per_chunk * 4, ev0 = (uint64_t)(uintptr_t)p.events, ev1 = ev0 + p.nchunks * list_bytes - 1;
     lean = ((list_bytes & (list_bytes - 1)) == 0 && ev0 % list_bytes == 0) || (ev0 >> 32) == (ev1 >> 32);
   }

@@ -96,7 +96,7 @@ struct _ac_machine {
   uint64_t device_generation;
   char engine_override[16];
   uint64_t option_bloom_words, option_threads, option_stream_bytes;
-  int option_no_stride2, option_no_events, option_no_tma, option_no_lean;
+  int option_no_stride2, option_no_events, option_no_tma, option_lean;
   uint64_t option_s2_smem_kb, option_s2_batches, option_s2_dist_log2;
   int force_rebuild;   /* an option that shapes the tables changed: the next finalise builds them from scratch */
   int option_no_patch; /* 0: tables are patched in place after append-only insertions where possible */

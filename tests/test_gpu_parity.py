@@ -365,15 +365,16 @@ def test_dfa_second_pass_from_recorded_events(novel):
     flat, offsets = pack(words)
     text = generate_text(3 << 20, kind=1, plant_period=512, dict_flat=flat, dict_offsets=offsets)
     want = oracle_records(words, text=text, kind="port")
-    for events in (1, 0):
+    for events, lean in ((1, 0), (1, 1), (0, 0)):
         m = ac75().Machine(1)
         m.insert_many(words)
         m.set_option("engine", "dfa_smem")
         m.set_option("dfa_events", events)
+        m.set_option("dfa_lean", lean)  # 1: pass 1 records events only, the records are counted from the event lists afterwards
         got = m.scan(text, capacity=1 << 22)
         lead_got = m.scan(text, lead=100_001, base=7, capacity=1 << 22)
         st = m.stats()
-        assert st["engine"] == "dfa_smem" and st["dfa_event_scans"] == (2 if events else 0), st
+        assert st["engine"] == "dfa_smem" and st["dfa_event_scans"] == (2 if events else 0) and (st["dfa_lean_scans"] > 0) == bool(lean), st
         assert len(want) > 100_000 and np.array_equal(got, want)
         w2 = want[want["end"] >= 100_001].copy()
         w2["end"] += 7
