@@ -491,6 +491,12 @@ encode_chunk_tensor (CUtensorMap *map, const void *text, uint64_t chunk, uint64_
 /* ---- device scan of counts ------------------------------------------------------------------------------------------ */
 static int
 device_exclusive_scan (ScanContext *cx, const uint32_t *counts, uint64_t n, uint64_t *offsets, uint64_t *d_grand, cudaStream_t st) {
+  if (n <= kScanSmall) {
+    scan_small_kernel<<<1, kScanThreads, 0, st>>> (counts, n, offsets, d_grand);
+    cx->stats.total_kernel_launches += 1;
+    CUDA_TRY (cudaGetLastError ());
+    return ACM_B200_OK;
+  }
   const uint64_t nblocks = (n + kScanBlock - 1) / kScanBlock;
   int rc = cx->d_block_sums.ensure ((nblocks + 1) * 8);
   if (rc)

@@ -70,6 +70,29 @@ block_exclusive_scan (uint64_t v, uint64_t *total, uint64_t *warp_sums /* [32] s
   return r;
 }
 
+/* Up to kScanSmall counts: the whole scan in one block (a 1 GiB shard of a strong-scaling run has 32 Ki spans; three launches
+ * were a fifth of what its scan costs beside the streaming kernel). */
+constexpr uint64_t kScanSmall = 32768;
+__global__ void __launch_bounds__ (kScanThreads)
+scan_small_kernel (const uint32_t *__restrict__ counts, uint64_t n, uint64_t *__restrict__ offsets, uint64_t *__restrict__ grand) {
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t total;
+  const uint32_t per = (uint32_t)((n + kScanThreads - 1) / kScanThreads); /* consecutive counts per thread, <= 32 */
+  const uint64_t base = (uint64_t)threadIdx.x * per;
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < per; i++)
+    if (base + i < n)
+      v += counts[base + i];
+  uint64_t ex = block_exclusive_scan (v, &total, warp_sums);
+  for (uint32_t i = 0; i < per; i++)
+    if (base + i < n) {
+      offsets[base + i] = ex;
+      ex += counts[base + i];
+    }
+  if (threadIdx.x == 0)
+    *grand = total;
+}
+
 __global__ void __launch_bounds__ (kScanThreads)
 scan_block_sums_kernel (const uint32_t *__restrict__ counts, uint64_t n, uint64_t *__restrict__ block_sums) {
   __shared__ uint64_t warp_sums[32];
@@ -854,6 +877,20 @@ struct FilterParams {
   unsigned long long *span_counter;
 };
 
+/* The filter of a CTA, global -> shared memory, 16 bytes per load (both sides are 16-byte aligned; the last words one by one):
+ * word by word the 175 KB took 43 rounds of dependent loads per thread, a fixed ~10 us of every scan. */
+__device__ __forceinline__ void
+copy_words_to_shared (uint32_t *dst, const uint32_t *__restrict__ src, uint32_t nwords) {
+  const uint32_t nvec = nwords / 4;
+  const uint4 *src4 = reinterpret_cast<const uint4 *> (src);
+  uint4 *dst4 = reinterpret_cast<uint4 *> (dst);
+#pragma unroll 4
+  for (uint32_t i = threadIdx.x; i < nvec; i += blockDim.x)
+    dst4[i] = __ldg (src4 + i);
+  for (uint32_t i = nvec * 4 + threadIdx.x; i < nwords; i += blockDim.x)
+    dst[i] = src[i];
+}
+
 template <int W> struct SymT;
 template <> struct SymT<1> { typedef uint8_t type; };
 template <> struct SymT<2> { typedef uint16_t type; };
@@ -973,8 +1010,7 @@ filter_scan_kernel (const __grid_constant__ FilterParams p) {
   extern __shared__ __align__ (16) unsigned char smem[];
   uint32_t *s_bloom = reinterpret_cast<uint32_t *> (smem);
   unsigned char *s_stage_all = smem + (size_t)p.bloom_words * 4;
-  for (uint32_t i = threadIdx.x; i < p.bloom_words; i += blockDim.x)
-    s_bloom[i] = p.bloom[i];
+  copy_words_to_shared (s_bloom, p.bloom, p.bloom_words);
   __syncthreads ();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -1372,8 +1408,7 @@ filter_scan_s2_kernel (const __grid_constant__ FilterParams p) {
   constexpr uint32_t kSpanTiles = kS2SpanBytes / kTileBytes;
   extern __shared__ __align__ (16) unsigned char smem[];
   uint32_t *s_bloom = reinterpret_cast<uint32_t *> (smem);
-  for (uint32_t i = threadIdx.x; i < p.bloom_s2_words; i += blockDim.x)
-    s_bloom[i] = p.bloom_s2[i];
+  copy_words_to_shared (s_bloom, p.bloom_s2, p.bloom_s2_words);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t kHitCap = p.s2_hit_cap; /* 1.5x the expected hits per tile + 32, see acm_finalise.c */
