@@ -172,6 +172,14 @@ class Machine:
         _check(lib().acm_b200_get_stats(self._m, ctypes.byref(s)))
         return s.as_dict()
 
+    def stats_into(self, s=None):
+        """Fills a Stats structure in place (a new one if none is given) and returns it -- no dictionary: for timed loops, where host
+        time between two scans is GPU idle time."""
+        if s is None:
+            s = Stats()
+        _check(lib().acm_b200_get_stats(self._m, ctypes.byref(s)))
+        return s
+
     def reset_cursor(self):
         self._cursor = ctypes.c_void_p(lib().acm_initiate(self._m))
 

@@ -309,15 +309,16 @@ def measure(name, cfg, args, ac75, torch, dist, rank, world, local, scaling, ste
     t_begin = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     main_ms, kernel_ms, cands = [], [], 0
+    raw = m.stats_into()  # refilled in place below: the scan call synchronises, so every microsecond of host work between two scans is GPU idle time
     ev0.record(stream)
     for _ in range(steps):
         local_matches = step_device()
         exchange(local_matches)
-        s = m.stats()
-        main_ms.append(s["main_kernel_ms"])
-        kernel_ms.append(s["scan_kernel_ms"])
-        cands = s["last_nb_candidates"]
+        m.stats_into(raw)
+        main_ms.append(raw.main_kernel_ms)
+        kernel_ms.append(raw.scan_kernel_ms)
     ev1.record(stream)
+    cands = raw.last_nb_candidates
     barrier()
     clocks = sampler.stop(t_begin, time.time())
     st1 = m.stats()
