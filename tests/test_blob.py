@@ -42,6 +42,20 @@ def test_load_rejects_what_is_not_a_blob(tmp_path):
         ac75().Machine.load(bad)
     with pytest.raises(ac75().AcmError):
         ac75().Machine.load(tmp_path / "missing.ac75")
+    # a blob of another format version (its tables may be hashed differently: version 3 changed the slot hash) is refused, not misread
+    m = ac75().Machine(1)
+    m.insert_many([b"abcde", b"bcdef", b"xyz12"])
+    good = tmp_path / "good.ac75"
+    m.save(good)
+    m.close()
+    ac75().Machine.load(good).close()
+    raw = bytearray(good.read_bytes())
+    version = int.from_bytes(raw[8:12], "little")
+    raw[8:12] = (version - 1).to_bytes(4, "little")
+    old = tmp_path / "old.ac75"
+    old.write_bytes(bytes(raw))
+    with pytest.raises(ac75().AcmError):
+        ac75().Machine.load(old)
 
 
 @pytest.mark.gpu
