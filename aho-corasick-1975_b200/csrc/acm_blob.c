@@ -116,7 +116,15 @@ acm_b200_save (ACMachine *m, const char *path) {
     goto done;
   struct blob_array arr[32];
   const int na = blob_arrays (&t, arr);
-  int ok = put (f, &h, sizeof h) && put (f, offsets, (nk + 1) * sizeof (*offsets)) && put (f, symbols, total * w) && put (f, &t, sizeof t);
+  struct acm_tables image = t; /* the scalar fields; this process's pointers mean nothing to a reader and would make equal dictionaries give different files */
+  {
+    struct blob_array image_arr[32];
+    const int ni = blob_arrays (&image, image_arr);
+    for (int i = 0; i < ni; i++)
+      *image_arr[i].ptr = 0;
+    image.builder = 0;
+  }
+  int ok = put (f, &h, sizeof h) && put (f, offsets, (nk + 1) * sizeof (*offsets)) && put (f, symbols, total * w) && put (f, &image, sizeof image);
   for (int i = 0; i < na && ok; i++) {
     const uint64_t bytes = *arr[i].ptr ? arr[i].bytes : 0;
     ok = put (f, &bytes, sizeof bytes) && put (f, *arr[i].ptr, bytes);

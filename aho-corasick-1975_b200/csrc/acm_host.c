@@ -59,11 +59,51 @@ compare_letters (const struct _ac_machine *m, const void *a, const void *b) {
   }
 }
 
+/* ACM_CMP_DEFAULT over 1/2/4-byte letters: the letter as an integer whose order is the comparator's (memcmp) order.  A state with
+ * more than one child keeps these keys right behind its child pointers (one allocation), so that looking a letter up reads one
+ * contiguous array instead of two dependent cache lines per probe (child state, then its letter): acm_find_child was 58 % of the
+ * time it takes to load 10^6 keywords. */
+static inline int
+raw_letters (const struct _ac_machine *m) {
+  return m->symbol_kind == ACM_SYM_RAW1 || m->symbol_kind == ACM_SYM_RAW2 || m->symbol_kind == ACM_SYM_RAW4;
+}
+
+static inline uint32_t
+letter_key (const struct _ac_machine *m, const void *letter) {
+  const unsigned char *b = letter;
+  switch (m->symbol_kind) {
+    case ACM_SYM_RAW1:
+      return b[0];
+    case ACM_SYM_RAW2:
+      return ((uint32_t)b[0] << 8) | b[1];
+    default:
+      return ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+  }
+}
+
+static inline uint32_t *
+child_keys (const struct _ac_state *s) { /* only for heap-allocated child arrays of raw-letter machines */
+  return (uint32_t *)(s->children + s->cap_children);
+}
+
 /* Position of `letter` among the children of s: index of the match, or ~(insertion point). */
 static inline int64_t
 child_slot (const struct _ac_state *s, const void *letter) {
   const struct _ac_machine *m = s->machine;
   uint32_t lo = 0, hi = s->nb_children;
+  if (s->children != &s->inline_child && raw_letters (m)) {
+    const uint32_t key = letter_key (m, letter), *keys = child_keys (s);
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (keys[mid] == key)
+        return mid;
+      if (key < keys[mid])
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    return ~(int64_t)lo;
+  }
   while (lo < hi) {
     uint32_t mid = lo + (hi - lo) / 2;
     int c = compare_letters (m, letter, s->children[mid]->letter);
@@ -119,10 +159,23 @@ new_state (struct _ac_machine *m) {
 
 static void
 add_child (struct _ac_state *s, struct _ac_state *child, uint32_t at) {
+  const int keyed = raw_letters (s->machine);
   if (s->nb_children == s->cap_children) {
     uint32_t cap = s->cap_children * 2;
     struct _ac_state **grown;
-    if (s->children == &s->inline_child) {
+    if (keyed) { /* pointers, then keys: a new block, both arrays copied over */
+      grown = malloc (cap * (sizeof (*grown) + sizeof (uint32_t)));
+      REQUIRE (grown, "Out of memory.");
+      uint32_t *keys = (uint32_t *)(grown + cap);
+      if (s->children == &s->inline_child) {
+        grown[0] = s->inline_child;
+        keys[0] = letter_key (s->machine, s->inline_child->letter);
+      } else {
+        memcpy (grown, s->children, s->nb_children * sizeof (*grown));
+        memcpy (keys, child_keys (s), s->nb_children * sizeof (uint32_t));
+        free (s->children);
+      }
+    } else if (s->children == &s->inline_child) {
       grown = malloc (cap * sizeof (*grown));
       if (grown)
         grown[0] = s->inline_child;
@@ -134,6 +187,11 @@ add_child (struct _ac_state *s, struct _ac_state *child, uint32_t at) {
   }
   memmove (s->children + at + 1, s->children + at, (s->nb_children - at) * sizeof (*s->children));
   s->children[at] = child;
+  if (keyed && s->children != &s->inline_child) {
+    uint32_t *keys = child_keys (s);
+    memmove (keys + at + 1, keys + at, (s->nb_children - at) * sizeof (uint32_t));
+    keys[at] = letter_key (s->machine, child->letter);
+  }
   s->nb_children++;
 }
 

@@ -49,6 +49,13 @@ def test_load_rejects_what_is_not_a_blob(tmp_path):
     m.save(good)
     m.close()
     ac75().Machine.load(good).close()
+    # equal dictionaries give equal files (no pointer of the saving process is written)
+    m2 = ac75().Machine(1)
+    m2.insert_many([b"abcde", b"bcdef", b"xyz12"])
+    again = tmp_path / "again.ac75"
+    m2.save(again)
+    m2.close()
+    assert again.read_bytes() == good.read_bytes()
     raw = bytearray(good.read_bytes())
     version = int.from_bytes(raw[8:12], "little")
     raw[8:12] = (version - 1).to_bytes(4, "little")
